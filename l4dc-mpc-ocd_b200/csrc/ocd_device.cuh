@@ -1,0 +1,449 @@
+// ocd_device.cuh -- device-side math of the batched MPC engine (sm_100a).
+//
+// One thread owns one (problem, start) pair and keeps the whole trajectory optimisation in
+// registers: controls, saved forward quantities and feature gradients for all H steps.  The
+// forward rollout evaluates the feature GRADIENT at each new state (the reward value itself is
+// only needed once, for the final loss), the reverse sweep is the closed-form adjoint of the
+// car dynamics, and the SGD update is applied in the same sweep.  What each block shares --
+// the other cars' predicted positions and the raw weight vectors -- lives in shared memory.
+//
+// Reference semantics implemented here (paths relative to the reference checkout):
+//   dynamics            interact_drive/simulation_utils.py:9-21
+//   smooth helpers      interact_drive/math_utils.py:7-31, 59-97, 135-180
+//   features            experiments/merging.py:32-83 ; interact_drive/world.py:206-218
+//   reward              interact_drive/car/linear_reward_car.py:49-55
+//   other-car model     interact_drive/planner/naive_planner.py:47-67
+//   rollout + SGD       interact_drive/planner/naive_planner.py:32-79, 107-164
+// Gradient conventions are TensorFlow 2.1's: clip masks inclusive, Minimum
+// passes on <=, reduce_min/max split evenly among ties, where() blocks the unselected branch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ocd_b200.h"
+
+namespace ocd {
+
+// Device-side digest of ocd_params: every Python-float constant already cast to float32 the
+// way TensorFlow casts it at op time.
+struct KParams {
+    int   H, NO, L, K, n_iter, S, other_mode, extra_inits;
+    float lr, dt, dt2, hdt2;      // dt2 = (float)(dt*dt) squared in double; hdt2 = 0.5f*dt2
+    float mu, ts, bound;          // friction, target speed, 4*ts^2
+    float thr_lo, thr_w, fshape;  // fence ramp: |x| in [thr_lo, thr_lo + thr_w], shape = 5/width
+    float turn;                   // 5*0.13 start angular velocity
+    float lane_x[OCD_MAX_LANES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Math back-ends.  FAST: one MUFU op per transcendental (sin/cos/ex2/rcp .approx).  PRECISE:
+// libdevice sinf/cosf/expf and IEEE division, op order as in the reference.
+// ---------------------------------------------------------------------------------------------
+template <bool PRECISE>
+struct Mth;
+
+template <>
+struct Mth<false> {
+    static __device__ __forceinline__ void sincos_(float th, float &s, float &c) {
+        s = __sinf(th);
+        c = __cosf(th);
+    }
+    static __device__ __forceinline__ float rcp_(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float exp_(float x) {   // e^x
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        return r;
+    }
+    static __device__ __forceinline__ float div_(float a, float b) { return a * rcp_(b); }
+};
+
+template <>
+struct Mth<true> {
+    static __device__ __forceinline__ void sincos_(float th, float &s, float &c) {
+        s = sinf(th);
+        c = cosf(th);
+    }
+    static __device__ __forceinline__ float rcp_(float x) { return __fdiv_rn(1.0f, x); }
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// a1  car_dynamics_step (simulation_utils.py:9-21), one car.
+// ---------------------------------------------------------------------------------------------
+template <bool PRECISE>
+__device__ __forceinline__ void dynamics_step(float &x, float &y, float &v, float &th, float a, float om,
+                                              float dt, float dt2, float mu) {
+    const float ac = fmaxf(fminf(a, 4.0f), -8.0f);
+    const float oc = fmaxf(fminf(om, 4.0f), -4.0f);
+    float sn, cs;
+    Mth<PRECISE>::sincos_(th, sn, cs);
+    if (PRECISE) {   // one rounding per reference op
+        const float total = __fsub_rn(ac, __fmul_rn(mu, __fmul_rn(v, v)));
+        const float dist = __fadd_rn(__fmul_rn(v, dt), __fmul_rn(__fmul_rn(0.5f, total), dt2));
+        x = __fadd_rn(x, __fmul_rn(cs, dist));
+        y = __fadd_rn(y, __fmul_rn(sn, dist));
+        v = __fadd_rn(v, __fmul_rn(total, dt));
+        th = __fadd_rn(th, __fmul_rn(oc, dt));
+    } else {
+        const float total = fmaf(-mu, v * v, ac);
+        const float dist = fmaf(total, 0.5f * dt2, v * dt);
+        x = fmaf(cs, dist, x);
+        y = fmaf(sn, dist, y);
+        v = fmaf(total, dt, v);
+        th = fmaf(oc, dt, th);
+    }
+}
+
+// Planner's model of another car (naive_planner.py:53-66): frictionless, unclipped.
+template <bool PRECISE>
+__device__ __forceinline__ void other_model_step(float &x, float &y, float &v, float &th, bool known,
+                                                 float a, float om, float dt, float dt2) {
+    float sn, cs;
+    Mth<PRECISE>::sincos_(th, sn, cs);
+    if (known) {
+        const float dist = __fadd_rn(__fmul_rn(v, dt), __fmul_rn(__fmul_rn(0.5f, a), dt2));
+        x = __fadd_rn(x, __fmul_rn(cs, dist));
+        y = __fadd_rn(y, __fmul_rn(sn, dist));
+        v = __fadd_rn(v, __fmul_rn(a, dt));
+        th = __fadd_rn(th, __fmul_rn(om, dt));
+    } else {
+        x = __fadd_rn(x, __fmul_rn(__fmul_rn(cs, v), dt));
+        y = __fadd_rn(y, __fmul_rn(__fmul_rn(sn, v), dt));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Smooth helpers (math_utils.py).  Each returns the value and its derivative.
+// ---------------------------------------------------------------------------------------------
+// smooth_bump(c - hw, c + hw)(z): value b and db/dz.  FAST uses c and 1/hw directly; PRECISE
+// recomputes width and center from start/end in float32 like math_utils.py:169-171.
+template <bool PRECISE>
+__device__ __forceinline__ void bump_vg(float z, float c, float hw, float inv_hw, float &b, float &db) {
+    float n, iw;
+    if (PRECISE) {
+        const float start = __fsub_rn(c, hw), end = __fadd_rn(c, hw);
+        const float width = __fmul_rn(__fsub_rn(end, start), 0.5f);
+        const float center = __fmul_rn(__fadd_rn(start, end), 0.5f);
+        n = __fdiv_rn(__fsub_rn(z, center), width);
+        iw = __fdiv_rn(1.0f, width);
+    } else {
+        n = (z - c) * inv_hw;
+        iw = inv_hw;
+    }
+    const float om = fmaf(-n, n, 1.0f);
+    b = 0.0f;
+    db = 0.0f;
+    if (n * n < 1.0f) {
+        const float r = Mth<PRECISE>::rcp_(om);
+        b = Mth<PRECISE>::exp_(1.0f - r);
+        db = b * (-2.0f * n) * (r * r) * iw;
+    }
+}
+
+// fence(x) = (T(x) + T(-x)) * |x| with T = smooth_threshold(0.05*num_lanes, 0.05)
+// (merging.py:80-81).  T(-|x|) is identically 0 (its _f argument is <= 0), so the feature is
+// T(|x|)*|x|: 0 below the ramp, |x| above it, two exponentials only inside the ramp.
+template <bool PRECISE>
+__device__ __forceinline__ void fence_vg(const KParams &k, float x, float &f, float &df) {
+    const float ax = fabsf(x);
+    const float q = ax - k.thr_lo;
+    const float u2 = k.thr_w - q;
+    const float sg = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+    f = 0.0f;
+    df = 0.0f;
+    if (q > 0.0f) {
+        if (u2 > 0.0f) {
+            const float r1 = Mth<PRECISE>::rcp_(k.fshape * q);
+            const float r2 = Mth<PRECISE>::rcp_(k.fshape * u2);
+            const float F1 = Mth<PRECISE>::exp_(-r1);
+            const float F2 = Mth<PRECISE>::exp_(-r2);
+            const float inv = Mth<PRECISE>::rcp_(F1 + F2);
+            const float T = F1 * inv;
+            // F'(q) = F(q)/(shape q^2) = F * shape * r^2
+            const float dT = (F1 * F2) * (k.fshape * fmaf(r1, r1, r2 * r2)) * (inv * inv);
+            f = T * ax;
+            df = sg * fmaf(dT, ax, T);
+        } else {
+            f = ax;
+            df = sg;
+        }
+    }
+}
+
+// Per-problem weights, pre-combined for the gradient:
+//   sum_i w_i * d/dx[10 (x-l_i)^2] = GA*x + GB ;  w0x2 = 2 w_speed ; wmin20 = 20 w_min
+struct GradW {
+    float w0x2, GA, GB, wmin20, wcol, wfence;
+};
+
+__device__ __forceinline__ GradW make_gradw(const KParams &k, const float *w /*[K] stride ws*/, int ws) {
+    GradW g;
+    g.w0x2 = 2.0f * w[0];
+    float sa = 0.0f, sb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < OCD_MAX_LANES; ++i)
+        if (i < k.L) {
+            const float wi = w[(1 + i) * ws];
+            sa += wi;
+            sb = fmaf(wi, k.lane_x[i], sb);
+        }
+    g.GA = 20.0f * sa;
+    g.GB = -20.0f * sb;
+    g.wmin20 = 20.0f * w[(1 + k.L) * ws];
+    g.wcol = w[(2 + k.L) * ws];
+    g.wfence = w[(3 + k.L) * ws];
+    return g;
+}
+
+// Gradient of w.phi with respect to the robot state (x, y, v, th) at one world state.
+//   oth: other cars' positions, x of car j at oth[j*jstride], y at oth[j*jstride + cstride].
+template <int NOT_, bool PRECISE>
+__device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
+                                             float sn, float cs, const float *oth, int jstride, int cstride,
+                                             float &gx, float &gy, float &gv, float &gth) {
+    const int NO = NOT_ > 0 ? NOT_ : k.NO;
+    // speed: min((v sin th - ts)^2, 4 ts^2)                                  merging.py:58-59
+    {
+        const float e = fmaf(v, sn, -k.ts);
+        const float ke = (e * e <= k.bound) ? (w.w0x2 * e) : 0.0f;
+        gv = ke * sn;
+        gth = ke * v * cs;
+    }
+    // lanes: sum_i w_i 10 (x - l_i)^2 and the min over lanes                 merging.py:61-65
+    gx = fmaf(w.GA, x, w.GB);
+    {
+        float fbest = 0.0f, sum = 0.0f, cnt = 1.0f;
+#pragma unroll
+        for (int i = 0; i < OCD_MAX_LANES; ++i)
+            if (i < k.L) {
+                const float dx = x - k.lane_x[i];
+                const float f = (dx * dx) * 10.0f;
+                if (i == 0 || f < fbest) {
+                    fbest = f; sum = dx; cnt = 1.0f;
+                } else if (f == fbest) {
+                    sum += dx; cnt += 1.0f;
+                }
+            }
+        if (cnt != 1.0f) sum = __fdiv_rn(sum, cnt);
+        gx = fmaf(w.wmin20, sum, gx);
+    }
+    // collision: max_j bump_x * bump_y                                        merging.py:67-78
+    {
+        float best = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
+#pragma unroll
+        for (int j = 0; j < (NOT_ > 0 ? NOT_ : OCD_MAX_OTHER); ++j)
+            if (j < NO) {
+                const float ox = oth[j * jstride], oy = oth[j * jstride + cstride];
+                float val = 0.0f, vx = 0.0f, vy = 0.0f;
+                if (PRECISE) {
+                    float bx, dbx, by, dby;
+                    bump_vg<true>(x, ox, 0.08f, 12.5f, bx, dbx);
+                    bump_vg<true>(y, oy, 0.15f, 6.6666667f, by, dby);
+                    val = bx * by; vx = dbx * by; vy = bx * dby;
+                } else {
+                    // both bumps share one exponential: bx*by = exp(2 - 1/(1-nx^2) - 1/(1-ny^2))
+                    const float nx = (x - ox) * 12.5f, ny = (y - oy) * 6.6666667f;
+                    const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
+                    if (ux > 0.0f && uy > 0.0f) {
+                        const float rx = Mth<false>::rcp_(ux), ry = Mth<false>::rcp_(uy);
+                        val = Mth<false>::exp_(2.0f - rx - ry);
+                        vx = val * (-25.0f * nx) * (rx * rx);          // -2 n r^2 / 0.08
+                        vy = val * (-13.333333f * ny) * (ry * ry);     // -2 n r^2 / 0.15
+                    }
+                }
+                if (j == 0 || val > best) {
+                    best = val; sx = vx; sy = vy; cnt = 1.0f;
+                } else if (val == best) {
+                    sx += vx; sy += vy; cnt += 1.0f;
+                }
+            }
+        if (cnt != 1.0f) {
+            sx = __fdiv_rn(sx, cnt);
+            sy = __fdiv_rn(sy, cnt);
+        }
+        gx = fmaf(w.wcol, sx, gx);
+        gy = w.wcol * sy;
+    }
+    // fence                                                                    merging.py:80-81
+    {
+        float f, df;
+        fence_vg<PRECISE>(k, x, f, df);
+        gx = fmaf(w.wfence, df, gx);
+    }
+}
+
+// Feature vector phi[K] at one world state, in the reference's order and op order.
+template <bool PRECISE>
+__device__ __forceinline__ void feature_values(const KParams &k, float x, float y, float v, float sn,
+                                               const float *oth, int jstride, int cstride,
+                                               float (&phi)[OCD_MAX_LANES + 4]) {
+    {
+        const float e = __fsub_rn(__fmul_rn(v, sn), k.ts);
+        phi[0] = fminf(__fmul_rn(e, e), k.bound);
+    }
+    float fmin_ = 0.0f;
+#pragma unroll
+    for (int i = 0; i < OCD_MAX_LANES; ++i)
+        if (i < k.L) {
+            const float dx = x - k.lane_x[i];
+            const float f = __fmul_rn(__fmul_rn(dx, dx), 10.0f);
+            phi[1 + i] = f;
+            fmin_ = (i == 0) ? f : fminf(fmin_, f);
+        }
+    float best = 0.0f;
+    for (int j = 0; j < k.NO; ++j) {
+        const float ox = oth[j * jstride], oy = oth[j * jstride + cstride];
+        float bx, dbx, by, dby;
+        bump_vg<PRECISE>(x, ox, 0.08f, 12.5f, bx, dbx);
+        bump_vg<PRECISE>(y, oy, 0.15f, 6.6666667f, by, dby);
+        const float val = __fmul_rn(bx, by);
+        best = (j == 0) ? val : fmaxf(best, val);
+    }
+    float fen, dfen;
+    fence_vg<PRECISE>(k, x, fen, dfen);
+    // write the tail with static indices only (phi stays in registers)
+#pragma unroll
+    for (int i = 1; i <= OCD_MAX_LANES; ++i)
+        if (i == k.L) {
+            phi[1 + i] = fmin_;
+            if (i + 2 < OCD_MAX_LANES + 4) phi[2 + i] = best;
+            if (i + 3 < OCD_MAX_LANES + 4) phi[3 + i] = fen;
+        }
+}
+
+// w . phi summed in feature order (linear_reward_car.py:53).  w[k] at w[k*ws].
+template <bool PRECISE>
+__device__ __forceinline__ float reward_value(const KParams &k, const float *w, int ws, float x, float y,
+                                              float v, float sn, const float *oth, int jstride, int cstride) {
+    float phi[OCD_MAX_LANES + 4];
+    feature_values<PRECISE>(k, x, y, v, sn, oth, jstride, cstride, phi);
+    float r = 0.0f;
+#pragma unroll
+    for (int i = 0; i < OCD_MAX_LANES + 4; ++i)
+        if (i < k.K) r = __fadd_rn(r, __fmul_rn(w[i * ws], phi[i]));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One (problem, start): forward rollout + feature gradients, reverse adjoint sweep, SGD update.
+//   HT > 0: horizon known at compile time, everything unrolled into registers.
+//   HT == 0: runtime horizon (<= OCD_MAX_H), per-step arrays in local memory.
+// `oth` points at this problem's column of the block's other-car slab laid out
+// [H][NO][2][P]: position c of car j at step t is oth[((t*NO + j)*2 + c)*P].
+// ---------------------------------------------------------------------------------------------
+template <int HT>
+struct Traj {
+    static constexpr int HM = HT > 0 ? HT : OCD_MAX_H;
+    float ua[HM], uw[HM];                      // controls (acceleration, angular velocity)
+};
+
+template <int HT, int NOT_, bool PRECISE, bool UPDATE>
+__device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
+                                              float th0, float sn0, float cs0, const float *oth, int P,
+                                              Traj<HT> &u, float *ga_out, float *gw_out) {
+    constexpr int HM = Traj<HT>::HM;
+    const int H = HT > 0 ? HT : k.H;
+    const int NO = NOT_ > 0 ? NOT_ : k.NO;
+    float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
+    float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
+    float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
+#pragma unroll
+    for (int t = 0; t < HM; ++t)
+        if (t < H) {
+            const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
+            const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
+            const float total = fmaf(-k.mu, v * v, ac);
+            const float dist = fmaf(total, k.hdt2, v * k.dt);
+            sv[t] = v; sc[t] = cs; ss[t] = sn; sd[t] = dist;
+            x = fmaf(cs, dist, x);
+            y = fmaf(sn, dist, y);
+            v = fmaf(total, k.dt, v);
+            th = fmaf(oc, k.dt, th);
+            Mth<PRECISE>::sincos_(th, sn, cs);
+            feature_grad<NOT_, PRECISE>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
+                                        gx[t], gy[t], gv[t], gth[t]);
+        }
+    float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
+    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+#pragma unroll
+    for (int tt = 0; tt < HM; ++tt) {
+        const int t = (HT > 0 ? HT : H) - 1 - tt;
+        if (t >= 0) {
+            const float mx = gx[t] + lx, my = gy[t] + ly, mv = gv[t] + lv, mth = gth[t] + lth;
+            const float ld = fmaf(sc[t], mx, ss[t] * my);
+            const float a = u.ua[t], om = u.uw[t];
+            float ga = fmaf(k.hdt2, ld, k.dt * mv);
+            float gw = k.dt * mth;
+            ga = (a >= -8.0f && a <= 4.0f) ? ga : 0.0f;
+            gw = (om >= -4.0f && om <= 4.0f) ? gw : 0.0f;
+            lv = fmaf(fmaf(c1, sv[t], 1.0f), mv, fmaf(c2, sv[t], k.dt) * ld);
+            lth = fmaf(sd[t], fmaf(sc[t], my, -(ss[t] * mx)), mth);
+            lx = mx;
+            ly = my;
+            if (UPDATE) {                       // u <- u - lr * d(-R)/du          naive_planner.py:153
+                u.ua[t] = fmaf(k.lr, ga, a);
+                u.uw[t] = fmaf(k.lr, gw, om);
+            } else {
+                ga_out[t] = ga;
+                gw_out[t] = gw;
+            }
+        }
+    }
+}
+
+// R(u) = sum_t w . phi(s_{t+1}), value only, reference op order (naive_planner.py:43-77).
+template <int HT, bool PRECISE>
+__device__ __forceinline__ float rollout_reward(const KParams &k, const float *wraw, int ws, float x0, float y0,
+                                                float v0, float th0, const float *oth, int P,
+                                                const Traj<HT> &u) {
+    constexpr int HM = Traj<HT>::HM;
+    const int H = HT > 0 ? HT : k.H;
+    float x = x0, y = y0, v = v0, th = th0;
+    float r = 0.0f;
+#pragma unroll
+    for (int t = 0; t < HM; ++t)
+        if (t < H) {
+            dynamics_step<PRECISE>(x, y, v, th, u.ua[t], u.uw[t], k.dt, k.dt2, k.mu);
+            float sn, cs;
+            Mth<PRECISE>::sincos_(th, sn, cs);
+            r = __fadd_rn(r, reward_value<PRECISE>(k, wraw, ws, x, y, v, sn, oth + (size_t)t * k.NO * 2 * P,
+                                                   2 * P, P));
+        }
+    return r;
+}
+
+// Start s of the multi-start set (naive_planner.py:107-118).
+template <int HT>
+__device__ __forceinline__ void init_start(const KParams &k, int s, float cur_speed, Traj<HT> &u) {
+    const int H = HT > 0 ? HT : k.H;
+    const float a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(cur_speed, cur_speed)) : 0.0f;
+    const int m = s % 3;
+    const float w0 = (m == 0) ? 0.0f : ((m == 1) ? -k.turn : k.turn);
+#pragma unroll
+    for (int t = 0; t < Traj<HT>::HM; ++t)
+        if (t < H) {
+            u.ua[t] = a0;
+            u.uw[t] = w0;
+        }
+}
+
+// The complete solve for one (problem, start): n_iter SGD iterations, then the final loss.
+template <int HT, int NOT_, bool PRECISE>
+__device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, const float *wraw, int ws,
+                                             float x0, float y0, float v0, float th0, const float *oth, int P,
+                                             Traj<HT> &u) {
+    float sn0, cs0;
+    Mth<PRECISE>::sincos_(th0, sn0, cs0);
+#pragma unroll 1
+    for (int it = 0; it < k.n_iter; ++it)
+        sgd_iteration<HT, NOT_, PRECISE, true>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
+    return -rollout_reward<HT, PRECISE>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+}
+
+}  // namespace ocd
