@@ -1,0 +1,481 @@
+// ocd_api.cu -- C ABI of the B200-native batched MPC engine (libocd_b200.so): argument
+// validation, the (H, other cars, math mode) dispatch onto the kernels of ocd_kernels.cuh, the
+// operator kernels (reward + gradient, features, dynamics) and the host-buffer layer.
+// Build: make -C l4dc-mpc-ocd_b200/csrc   (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ocd_kernels.cuh"
+
+namespace ocd {
+
+// specialisations built by ocd_inst.cu
+#define OCD_EXTERN(HT, NO)                                                                                   \
+    extern template int launch_solve_t<HT, NO, false>(const KParams &, const SolveArgs &, cudaStream_t);     \
+    extern template int launch_solve_t<HT, NO, true>(const KParams &, const SolveArgs &, cudaStream_t);      \
+    extern template int launch_episode_t<HT, NO, false>(const KParams &, const ocd_scenario &,               \
+                                                        const EpisodeArgs &, cudaStream_t);                  \
+    extern template int launch_episode_t<HT, NO, true>(const KParams &, const ocd_scenario &,                \
+                                                       const EpisodeArgs &, cudaStream_t);
+OCD_EXTERN(5, 1)
+OCD_EXTERN(5, 2)
+OCD_EXTERN(5, 0)
+OCD_EXTERN(6, 1)
+OCD_EXTERN(3, 0)
+OCD_EXTERN(0, 0)
+#undef OCD_EXTERN
+
+// ---------------------------------------------------------------------------------------------
+// operator kernels: reward + gradient, features, dynamics
+// ---------------------------------------------------------------------------------------------
+template <bool PRECISE>
+__global__ void __launch_bounds__(128)
+k_reward_grad(const __grid_constant__ KParams k, const float *world, const float *controls,
+              const float *other_controls, long long Bo, const float *weights, long long Bw,
+              const int32_t *weight_idx, float *reward, float *grad, long long B) {
+    // one thread per problem; its slab column lives in local memory (runtime H, runtime NO)
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float oth[OCD_MAX_H * OCD_MAX_OTHER * 2];
+    // weights are read straight from global memory (element stride Bw).  A thread-local copy
+    // here was miscompiled by nvcc 12.9: the copy's stack slot was reused for reward_value's
+    // phi[] while make_gradw still reloaded it afterwards.
+    const float *w = weights + weight_column(weight_idx, Bw, b);
+    const int ws = (int)Bw;
+    for (int j = 0; j < k.NO; ++j) {
+        const float *st = world + (size_t)(j + 1) * 4 * B + b;
+        const float *oc = nullptr;
+        long long ocs = 0;
+        if (k.other_mode == 1) {
+            ocs = Bo;
+            oc = other_controls + (size_t)j * k.H * 2 * Bo + (Bo == 1 ? 0 : b);
+        }
+        predict_other<PRECISE>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, oth, j, 1);
+    }
+    const float x0 = world[b], y0 = world[B + b], v0 = world[2 * B + b], th0 = world[3 * B + b];
+    Traj<0> u;
+    for (int t = 0; t < k.H; ++t) {
+        u.ua[t] = controls[(size_t)(t * 2 + 0) * B + b];
+        u.uw[t] = controls[(size_t)(t * 2 + 1) * B + b];
+    }
+    reward[b] = rollout_reward<0, PRECISE>(k, w, ws, x0, y0, v0, th0, oth, 1, u);
+    if (grad) {
+        const GradW gw = make_gradw(k, w, ws);
+        float ga[OCD_MAX_H], go[OCD_MAX_H];
+        float sn0, cs0;
+        Mth<PRECISE>::sincos_(th0, sn0, cs0);
+        sgd_iteration<0, 0, PRECISE, false>(k, gw, x0, y0, v0, th0, sn0, cs0, oth, 1, u, ga, go);
+        for (int t = 0; t < k.H; ++t) {
+            grad[(size_t)(t * 2 + 0) * B + b] = ga[t];
+            grad[(size_t)(t * 2 + 1) * B + b] = go[t];
+        }
+    }
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(128)
+k_features(const __grid_constant__ KParams k, const float *world, float *phi, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float sn, cs;
+    Mth<PRECISE>::sincos_(world[3 * B + b], sn, cs);
+    float f[OCD_MAX_LANES + 4];
+    feature_values<PRECISE>(k, world[b], world[B + b], world[2 * B + b], sn, world + 4 * B + b,
+                            (int)(4 * B), (int)B, f);
+#pragma unroll
+    for (int i = 0; i < OCD_MAX_LANES + 4; ++i)
+        if (i < k.K) phi[(size_t)i * B + b] = f[i];
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(256)
+k_dynamics(const float *state, const float *control, float dt, float dt2, float friction,
+           const float *friction_b, float *next, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float x = state[b], y = state[B + b], v = state[2 * B + b], th = state[3 * B + b];
+    dynamics_step<PRECISE>(x, y, v, th, control[b], control[B + b], dt, dt2, friction_b ? friction_b[b] : friction);
+    next[b] = x; next[B + b] = y; next[2 * B + b] = v; next[3 * B + b] = th;
+}
+
+// dependent-free FMA loop: 8 independent chains per thread, 2 FLOP per FMA
+__global__ void __launch_bounds__(256) k_fp32_peak(int iters, float *sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) sink[0] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: parameter digest, validation, dispatch
+// ---------------------------------------------------------------------------------------------
+static int digest(const ocd_params *p, KParams &k) {
+    if (!p) return OCD_EINVAL;
+    if (p->H < 1 || p->C < 2 || p->L < 1 || p->n_iter < 0) return OCD_EINVAL;
+    if (p->H > OCD_MAX_H || p->C > OCD_MAX_OTHER + 1 || p->L > OCD_MAX_LANES) return OCD_EUNSUP;
+    if (p->other_mode != 0 && p->other_mode != 1) return OCD_EINVAL;
+    if (p->math_mode != 0 && p->math_mode != 1) return OCD_EINVAL;
+    std::memset(&k, 0, sizeof(k));
+    k.H = p->H;
+    k.NO = p->C - 1;
+    k.L = p->L;
+    k.K = p->L + 4;
+    k.n_iter = p->n_iter;
+    k.S = p->extra_inits ? 6 : 3;
+    k.other_mode = p->other_mode;
+    k.extra_inits = p->extra_inits ? 1 : 0;
+    k.lr = (float)p->lr;
+    k.dt = (float)p->dt;
+    k.dt2 = (float)(p->dt * p->dt);              // dt**2 in double, cast once (simulation_utils.py:16)
+    k.hdt2 = 0.5f * k.dt2;
+    k.mu = (float)p->friction;
+    k.ts = (float)p->target_speed;               // np.float32(target_speed), merging.py:49
+    k.bound = (float)(4.0 * (double)k.ts * (double)k.ts);
+    k.thr_lo = (float)(0.05 * (double)p->num_lanes - 0.05);   // threshold - width, math_utils.py:92
+    k.thr_w = 0.05f;
+    k.fshape = (float)(5.0 / 0.05);
+    k.turn = (float)(5 * 0.13);                  // naive_planner.py:109-110
+    for (int i = 0; i < p->L; ++i) k.lane_x[i] = (float)p->lane_x[i];
+    return OCD_OK;
+}
+
+static int check_weights(const float *weights, long long Bw, const int32_t *idx, long long B) {
+    if (!weights || Bw < 1) return OCD_EINVAL;
+    if (Bw > (1LL << 27)) return OCD_EUNSUP;   // (K-1)*Bw is indexed in 32 bits
+    if (!idx && Bw != 1 && Bw != B) return OCD_EINVAL;
+    return OCD_OK;
+}
+
+static int pick_P(long long B) {
+    // 64 problems per block once that still gives every SM several blocks; 32 below that
+    return B >= 64LL * 148 * 4 ? 64 : 32;
+}
+
+// (H, NO) specialisations: the shipped scenarios (H=5/6, one or two other cars), the planner
+// known-answer test (H=3) and a runtime-shape fallback.
+#define OCD_DISPATCH(FN, PRECISE, ...)                                                  \
+    do {                                                                                \
+        const int no = k.NO <= 2 ? k.NO : 0;                                            \
+        const int h = (k.H == 3 || k.H == 5 || (k.H == 6 && no == 1)) ? k.H : 0;        \
+        if (h == 5 && no == 1) return FN<5, 1, PRECISE>(__VA_ARGS__);                   \
+        if (h == 5 && no == 2) return FN<5, 2, PRECISE>(__VA_ARGS__);                   \
+        if (h == 5) return FN<5, 0, PRECISE>(__VA_ARGS__);                              \
+        if (h == 6 && no == 1) return FN<6, 1, PRECISE>(__VA_ARGS__);                   \
+        if (h == 3) return FN<3, 0, PRECISE>(__VA_ARGS__);                              \
+        return FN<0, 0, PRECISE>(__VA_ARGS__);                                          \
+    } while (0)
+
+static int launch_solve(const KParams &k, bool precise, const SolveArgs &a, cudaStream_t st) {
+    if (precise) OCD_DISPATCH(launch_solve_t, true, k, a, st);
+    OCD_DISPATCH(launch_solve_t, false, k, a, st);
+}
+
+static int launch_episode(const KParams &k, bool precise, const ocd_scenario &sc, const EpisodeArgs &a,
+                          cudaStream_t st) {
+    if (precise) OCD_DISPATCH(launch_episode_t, true, k, sc, a, st);
+    OCD_DISPATCH(launch_episode_t, false, k, sc, a, st);
+}
+
+}  // namespace ocd
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace ocd;
+
+extern "C" {
+
+int ocd_abi_version(void) { return OCD_ABI_VERSION; }
+
+const char *ocd_strerror(int code) {
+    switch (code) {
+        case OCD_OK: return "ok";
+        case OCD_EINVAL: return "invalid argument";
+        case OCD_EUNSUP: return "unsupported problem shape (H, C or L out of range)";
+        case OCD_ECUDA: return "CUDA error (no device, or launch/copy failure)";
+        case OCD_ENOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+int ocd_num_starts(const ocd_params *p) { return (p && p->extra_inits) ? 6 : 3; }
+
+int ocd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ocd_dynamics_step_batch(const float *state, const float *control, float dt, float friction,
+                            const float *friction_b, float *next_state, int64_t B, void *stream) {
+    if (B == 0) return OCD_OK;
+    if (!state || !control || !next_state || B < 0) return OCD_EINVAL;
+    const float dt2 = (float)((double)dt * (double)dt);
+    k_dynamics<true><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        state, control, dt, dt2, friction, friction_b, next_state, B);
+    return cuda_status();
+}
+
+int ocd_features_batch(const ocd_params *p, const float *world, float *phi, int64_t B, void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!world || !phi || B < 0) return OCD_EINVAL;
+    if (4 * B > 0x7fffffffLL) return OCD_EUNSUP;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (p->math_mode == 1) k_features<true><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, phi, B);
+    else k_features<false><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, phi, B);
+    return cuda_status();
+}
+
+int ocd_reward_grad_batch(const ocd_params *p, const float *world, const float *controls,
+                          const float *other_controls, int64_t Bo, const float *weights, int64_t Bw,
+                          const int32_t *weight_idx, float *reward, float *grad, int64_t B, void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!world || !controls || !reward || B < 0) return OCD_EINVAL;
+    if ((rc = check_weights(weights, Bw, weight_idx, B))) return rc;
+    if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
+    if (B == 0) return OCD_OK;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (p->math_mode == 1)
+        k_reward_grad<true><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo, weights,
+                                                                    Bw, weight_idx, reward, grad, B);
+    else
+        k_reward_grad<false><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo, weights,
+                                                                     Bw, weight_idx, reward, grad, B);
+    return cuda_status();
+}
+
+int ocd_solve_batch(const ocd_params *p, const float *world, const float *other_controls, int64_t Bo,
+                    const float *weights, int64_t Bw, const int32_t *weight_idx, const float *cur_speed,
+                    float *plan, float *losses, int32_t *best, float *all_plans, int64_t B, void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!world || !plan || !losses || !best || B < 0) return OCD_EINVAL;
+    if ((rc = check_weights(weights, Bw, weight_idx, B))) return rc;
+    if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
+    SolveArgs a{world, other_controls, Bo, weights, Bw, weight_idx, cur_speed, plan, losses, best, all_plans,
+                B, pick_P(B)};
+    return launch_solve(k, p->math_mode == 1, a, (cudaStream_t)stream);
+}
+
+int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc, const float *robot_init,
+                      const float *other_init, const float *plan_weights, int64_t Bw,
+                      const int32_t *weight_idx, const float *true_weights, const int32_t *unlucky_idx,
+                      int32_t t0, int32_t T, float *returns, float *traj_controls, int32_t *traj_best,
+                      float *traj_states, float *final_world, int64_t B, void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!sc || !robot_init || !true_weights || !returns || B < 0 || T < 0 || t0 < 0) return OCD_EINVAL;
+    if (sc->n_other != k.NO) return OCD_EINVAL;
+    for (int j = 0; j < k.NO; ++j)
+        if (sc->plan_len[j] < 0 || sc->plan_len[j] > OCD_MAX_PLAN || (sc->kind[j] != 0 && sc->kind[j] != 1))
+            return OCD_EINVAL;
+    if ((rc = check_weights(plan_weights, Bw, weight_idx, B))) return rc;
+    if (B == 0) return OCD_OK;
+    EpisodeArgs a{robot_init, other_init, plan_weights, Bw, weight_idx, true_weights, unlucky_idx, t0, T,
+                  returns, traj_controls, traj_best, traj_states, final_world, B, pick_P(B)};
+    return launch_episode(k, p->math_mode == 1, *sc, a, (cudaStream_t)stream);
+}
+
+// ---- host-buffer layer ------------------------------------------------------------------------
+struct ocd_ctx {
+    int device;
+    cudaStream_t stream;
+    char *dev;      size_t dev_cap;
+    char *pin;      size_t pin_cap;
+};
+
+static int ctx_reserve(ocd_ctx *c, size_t bytes) {
+    if (bytes > c->dev_cap) {
+        if (c->dev) cudaFree(c->dev);
+        c->dev = nullptr; c->dev_cap = 0;
+        if (cudaMalloc((void **)&c->dev, bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
+        c->dev_cap = bytes;
+    }
+    if (bytes > c->pin_cap) {
+        if (c->pin) cudaFreeHost(c->pin);
+        c->pin = nullptr; c->pin_cap = 0;
+        if (cudaMallocHost((void **)&c->pin, bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
+        c->pin_cap = bytes;
+    }
+    return OCD_OK;
+}
+
+int ocd_ctx_create(int device, ocd_ctx **out) {
+    if (!out) return OCD_EINVAL;
+    *out = nullptr;
+    if (device < 0 || device >= ocd_device_count()) return OCD_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return OCD_ECUDA;
+    ocd_ctx *c = new (std::nothrow) ocd_ctx();
+    if (!c) return OCD_ENOMEM;
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return OCD_ECUDA;
+    }
+    *out = c;
+    return OCD_OK;
+}
+
+void ocd_ctx_destroy(ocd_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->dev) cudaFree(c->dev);
+    if (c->pin) cudaFreeHost(c->pin);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// a tiny bump allocator over the ctx buffers: every array gets the same offset on the pinned
+// and on the device side, so one memcpy each way moves all inputs / all outputs.
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    }
+};
+
+int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
+                         int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
+                         const float *cur_speed, float *plan, float *losses, int32_t *best, int64_t B) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (!c || !world || !plan || !losses || !best || B < 0) return OCD_EINVAL;
+    if ((rc = check_weights(weights, Bw, weight_idx, B))) return rc;
+    if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
+    if (B == 0) return OCD_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) return OCD_ECUDA;
+    const int C = k.NO + 1;
+    Arena ar;
+    const size_t n_world = sizeof(float) * C * 4 * B, o_world = ar.take(n_world);
+    const size_t n_w = sizeof(float) * k.K * Bw, o_w = ar.take(n_w);
+    const size_t n_idx = weight_idx ? sizeof(int32_t) * B : 0, o_idx = ar.take(n_idx);
+    const size_t n_oc = k.other_mode == 1 ? sizeof(float) * k.NO * k.H * 2 * Bo : 0, o_oc = ar.take(n_oc);
+    const size_t n_cs = cur_speed ? sizeof(float) * B : 0, o_cs = ar.take(n_cs);
+    const size_t in_end = ar.off;
+    const size_t n_plan = sizeof(float) * k.H * 2 * B, o_plan = ar.take(n_plan);
+    const size_t n_loss = sizeof(float) * k.S * B, o_loss = ar.take(n_loss);
+    const size_t n_best = sizeof(int32_t) * B, o_best = ar.take(n_best);
+    if ((rc = ctx_reserve(c, ar.off))) return rc;
+    std::memcpy(c->pin + o_world, world, n_world);
+    std::memcpy(c->pin + o_w, weights, n_w);
+    if (n_idx) std::memcpy(c->pin + o_idx, weight_idx, n_idx);
+    if (n_oc) std::memcpy(c->pin + o_oc, other_controls, n_oc);
+    if (n_cs) std::memcpy(c->pin + o_cs, cur_speed, n_cs);
+    if (cudaMemcpyAsync(c->dev, c->pin, in_end, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return OCD_ECUDA;
+    rc = ocd_solve_batch(p, (const float *)(c->dev + o_world), n_oc ? (const float *)(c->dev + o_oc) : nullptr, Bo,
+                         (const float *)(c->dev + o_w), Bw, n_idx ? (const int32_t *)(c->dev + o_idx) : nullptr,
+                         n_cs ? (const float *)(c->dev + o_cs) : nullptr, (float *)(c->dev + o_plan),
+                         (float *)(c->dev + o_loss), (int32_t *)(c->dev + o_best), nullptr, B, c->stream);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(c->pin + o_plan, c->dev + o_plan, ar.off - o_plan, cudaMemcpyDeviceToHost, c->stream) !=
+        cudaSuccess)
+        return OCD_ECUDA;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
+    std::memcpy(plan, c->pin + o_plan, n_plan);
+    std::memcpy(losses, c->pin + o_loss, n_loss);
+    std::memcpy(best, c->pin + o_best, n_best);
+    return OCD_OK;
+}
+
+int ocd_episode_batch_host(ocd_ctx *c, const ocd_params *p, const ocd_scenario *sc, const float *robot_init,
+                           const float *other_init, const float *plan_weights, int64_t Bw,
+                           const int32_t *weight_idx, const float *true_weights, const int32_t *unlucky_idx,
+                           int32_t t0, int32_t T, float *returns, int64_t B) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (!c || !sc || !robot_init || !true_weights || !returns || B < 0) return OCD_EINVAL;
+    if ((rc = check_weights(plan_weights, Bw, weight_idx, B))) return rc;
+    if (B == 0) return OCD_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) return OCD_ECUDA;
+    Arena ar;
+    const size_t n_ri = sizeof(float) * 4 * B, o_ri = ar.take(n_ri);
+    const size_t n_oi = other_init ? sizeof(float) * k.NO * 4 * B : 0, o_oi = ar.take(n_oi);
+    const size_t n_w = sizeof(float) * k.K * Bw, o_w = ar.take(n_w);
+    const size_t n_idx = weight_idx ? sizeof(int32_t) * B : 0, o_idx = ar.take(n_idx);
+    const size_t n_tw = sizeof(float) * k.K, o_tw = ar.take(n_tw);
+    const size_t n_ul = unlucky_idx ? sizeof(int32_t) * B : 0, o_ul = ar.take(n_ul);
+    const size_t in_end = ar.off;
+    const size_t n_ret = sizeof(float) * B, o_ret = ar.take(n_ret);
+    if ((rc = ctx_reserve(c, ar.off))) return rc;
+    std::memcpy(c->pin + o_ri, robot_init, n_ri);
+    if (n_oi) std::memcpy(c->pin + o_oi, other_init, n_oi);
+    std::memcpy(c->pin + o_w, plan_weights, n_w);
+    if (n_idx) std::memcpy(c->pin + o_idx, weight_idx, n_idx);
+    std::memcpy(c->pin + o_tw, true_weights, n_tw);
+    if (n_ul) std::memcpy(c->pin + o_ul, unlucky_idx, n_ul);
+    if (cudaMemcpyAsync(c->dev, c->pin, in_end, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return OCD_ECUDA;
+    rc = ocd_episode_batch(p, sc, (const float *)(c->dev + o_ri), n_oi ? (const float *)(c->dev + o_oi) : nullptr,
+                           (const float *)(c->dev + o_w), Bw, n_idx ? (const int32_t *)(c->dev + o_idx) : nullptr,
+                           (const float *)(c->dev + o_tw), n_ul ? (const int32_t *)(c->dev + o_ul) : nullptr, t0, T,
+                           (float *)(c->dev + o_ret), nullptr, nullptr, nullptr, nullptr, B, c->stream);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(c->pin + o_ret, c->dev + o_ret, n_ret, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        return OCD_ECUDA;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
+    std::memcpy(returns, c->pin + o_ret, n_ret);
+    return OCD_OK;
+}
+
+int ocd_fp32_peak(int iters, double *flops, void *stream) {
+    if (!flops || iters < 1) return OCD_EINVAL;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return OCD_ECUDA;
+    float *sink = nullptr;
+    if (cudaMalloc((void **)&sink, sizeof(float)) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = sms * 8, threads = 256;
+    k_fp32_peak<<<blocks, threads, 0, st>>>(iters / 4 + 1, sink);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        k_fp32_peak<<<blocks, threads, 0, st>>>(iters, sink);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads / (ms * 1e-3);
+        if (fl > best) best = fl;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *flops = best;
+    return cuda_status() == OCD_OK && best > 0.0 ? OCD_OK : OCD_ECUDA;
+}
+
+}  // extern "C"

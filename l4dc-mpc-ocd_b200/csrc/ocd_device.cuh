@@ -236,9 +236,8 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
     // collision: max_j bump_x * bump_y                                        merging.py:67-78
     {
         float best = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
-#pragma unroll
-        for (int j = 0; j < (NOT_ > 0 ? NOT_ : OCD_MAX_OTHER); ++j)
-            if (j < NO) {
+#pragma unroll(NOT_ > 0 ? NOT_ : 1)
+        for (int j = 0; j < NO; ++j) {
                 const float ox = oth[j * jstride], oy = oth[j * jstride + cstride];
                 float val = 0.0f, vx = 0.0f, vy = 0.0f;
                 if (PRECISE) {
@@ -353,9 +352,8 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
     float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
     float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
     float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
-#pragma unroll
-    for (int t = 0; t < HM; ++t)
-        if (t < H) {
+#pragma unroll(HT > 0 ? HT : 1)
+    for (int t = 0; t < H; ++t) {
             const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
             const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
             const float total = fmaf(-k.mu, v * v, ac);
@@ -371,10 +369,10 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
         }
     float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
-#pragma unroll
-    for (int tt = 0; tt < HM; ++tt) {
-        const int t = (HT > 0 ? HT : H) - 1 - tt;
-        if (t >= 0) {
+#pragma unroll(HT > 0 ? HT : 1)
+    for (int tt = 0; tt < H; ++tt) {
+        const int t = H - 1 - tt;
+        {
             const float mx = gx[t] + lx, my = gy[t] + ly, mv = gv[t] + lv, mth = gth[t] + lth;
             const float ld = fmaf(sc[t], mx, ss[t] * my);
             const float a = u.ua[t], om = u.uw[t];
@@ -402,13 +400,11 @@ template <int HT, bool PRECISE>
 __device__ __forceinline__ float rollout_reward(const KParams &k, const float *wraw, int ws, float x0, float y0,
                                                 float v0, float th0, const float *oth, int P,
                                                 const Traj<HT> &u) {
-    constexpr int HM = Traj<HT>::HM;
     const int H = HT > 0 ? HT : k.H;
     float x = x0, y = y0, v = v0, th = th0;
     float r = 0.0f;
-#pragma unroll
-    for (int t = 0; t < HM; ++t)
-        if (t < H) {
+#pragma unroll(HT > 0 ? HT : 1)
+    for (int t = 0; t < H; ++t) {
             dynamics_step<PRECISE>(x, y, v, th, u.ua[t], u.uw[t], k.dt, k.dt2, k.mu);
             float sn, cs;
             Mth<PRECISE>::sincos_(th, sn, cs);
@@ -425,9 +421,8 @@ __device__ __forceinline__ void init_start(const KParams &k, int s, float cur_sp
     const float a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(cur_speed, cur_speed)) : 0.0f;
     const int m = s % 3;
     const float w0 = (m == 0) ? 0.0f : ((m == 1) ? -k.turn : k.turn);
-#pragma unroll
-    for (int t = 0; t < Traj<HT>::HM; ++t)
-        if (t < H) {
+#pragma unroll(HT > 0 ? HT : 1)
+    for (int t = 0; t < H; ++t) {
             u.ua[t] = a0;
             u.uw[t] = w0;
         }

@@ -1,0 +1,331 @@
+// ocd_kernels.cuh -- the two planner kernels of the batched MPC engine and their launchers.
+//
+//   k_solve    NaivePlanner.generate_plan for B problems: one thread per (problem, start); the
+//              block holds P problems x S starts, start-major (thread = s*P + p), so a warp runs
+//              one start of 32 consecutive problems and every global / shared access is
+//              coalesced / conflict-free in p.
+//   k_episode  MPC_ORD's receding-horizon loop for B worlds in ONE launch: per control step the
+//              block rebuilds the other cars' predicted tracks, runs the same solve, picks the
+//              first-minimum start, steps every car with the simulator dynamics and accumulates
+//              the true-weight reward of the past state.
+// Each (H, other cars, math mode) specialisation is instantiated in its own translation unit
+// (ocd_inst.cu compiled with -DOCD_HT/-DOCD_NO/-DOCD_PRECISE) so the library builds in parallel.
+// Reference lines for each piece are cited in ocd_device.cuh and include/ocd_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "ocd_b200.h"
+#include "ocd_device.cuh"
+
+namespace ocd {
+
+static constexpr int kMaxThreads = 384;   // S=6 starts x P=64 problems
+
+// ---------------------------------------------------------------------------------------------
+// argument blocks (passed by value as kernel parameters)
+// ---------------------------------------------------------------------------------------------
+struct SolveArgs {
+    const float *world;            // [C][4][B]
+    const float *other_controls;   // [NO][H][2][Bo] or null
+    long long    Bo;
+    const float *weights;          // [K][Bw]
+    long long    Bw;
+    const int32_t *weight_idx;     // [B] or null
+    const float *cur_speed;        // [B] or null
+    float       *plan;             // [H][2][B]
+    float       *losses;           // [S][B]
+    int32_t     *best;             // [B]
+    float       *all_plans;        // [S][H][2][B] or null
+    long long    B;
+    int          P;                // problems per block
+};
+
+struct EpisodeArgs {
+    const float *robot_init;       // [4][B]
+    const float *other_init;       // [NO][4][B] or null
+    const float *plan_weights;     // [K][Bw]
+    long long    Bw;
+    const int32_t *weight_idx;     // [B] or null
+    const float *true_weights;     // [K]
+    const int32_t *unlucky_idx;    // [B] or null
+    int          t0, T;
+    float       *returns;          // [B]
+    float       *traj_controls;    // [T][2][B] or null
+    int32_t     *traj_best;        // [T][B] or null
+    float       *traj_states;      // [T][C][4][B] or null
+    float       *final_world;      // [C][4][B] or null
+    long long    B;
+    int          P;
+};
+
+__device__ __forceinline__ long long weight_column(const int32_t *idx, long long Bw, long long b) {
+    if (idx) return (long long)idx[b];
+    return Bw == 1 ? 0 : b;
+}
+
+// shared-memory carve-up common to k_solve and k_episode (all float, P columns each)
+struct Smem {
+    float *oth;     // [H][NO][2][P]   other cars' predicted positions at steps 1..H
+    float *wraw;    // [K][P]          planning weights, raw feature order
+    float *loss;    // [S][P]
+    float *u0;      // [S][2][P]       first control of every start (episode only)
+    float *world;   // [C][4][P]       live world state (episode only)
+    float *wtrue;   // [K]             true weights (episode only)
+};
+
+__host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode) {
+    size_t n = (size_t)H * NO * 2 * P + (size_t)K * P + (size_t)S * P;
+    if (episode) n += (size_t)S * 2 * P + (size_t)(NO + 1) * 4 * P + K;
+    return n;
+}
+
+__device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool episode) {
+    Smem m;
+    m.oth = base;
+    m.wraw = m.oth + (size_t)k.H * k.NO * 2 * P;
+    m.loss = m.wraw + (size_t)k.K * P;
+    m.u0 = m.loss + (size_t)k.S * P;
+    m.world = episode ? m.u0 + (size_t)k.S * 2 * P : nullptr;
+    m.wtrue = episode ? m.world + (size_t)(k.NO + 1) * 4 * P : nullptr;
+    return m;
+}
+
+// The planner's prediction of other car j over the horizon (naive_planner.py:47-67), written to
+// the block slab.  (x, y, v, th) is the car's current state; oc = its known controls [H][2]
+// with element stride ocs, or null for the constant-velocity model.
+template <bool PRECISE>
+__device__ __forceinline__ void predict_other(const KParams &k, float x, float y, float v, float th,
+                                              const float *oc, long long ocs, float *oth_col, int j, int P) {
+    for (int t = 0; t < k.H; ++t) {
+        float a = 0.0f, om = 0.0f;
+        if (oc) {
+            a = oc[(size_t)(t * 2 + 0) * ocs];
+            om = oc[(size_t)(t * 2 + 1) * ocs];
+        }
+        other_model_step<PRECISE>(x, y, v, th, oc != nullptr, a, om, k.dt, k.dt2);
+        oth_col[(size_t)((t * k.NO + j) * 2 + 0) * P] = x;
+        oth_col[(size_t)((t * k.NO + j) * 2 + 1) * P] = y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_solve
+// ---------------------------------------------------------------------------------------------
+template <int HT, int NOT_, bool PRECISE>
+__global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
+    extern __shared__ float smem_raw[];
+    const int P = a.P;
+    const Smem m = carve(smem_raw, k, P, false);
+    const int p = threadIdx.x % P, s = threadIdx.x / P;
+    const long long b_raw = (long long)blockIdx.x * P + p;
+    const bool live = b_raw < a.B;
+    const long long b = live ? b_raw : a.B - 1;
+    const long long B = a.B;
+
+    if (s == 0) {
+        const long long wc = weight_column(a.weight_idx, a.Bw, b);
+        for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.weights[(size_t)i * a.Bw + wc];
+        for (int j = 0; j < k.NO; ++j) {
+            const float *st = a.world + (size_t)(j + 1) * 4 * B + b;
+            const float *oc = nullptr;
+            long long ocs = 0;
+            if (k.other_mode == 1) {
+                ocs = a.Bo;
+                oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
+            }
+            predict_other<PRECISE>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P);
+        }
+    }
+    __syncthreads();
+
+    const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
+    const GradW gw = make_gradw(k, m.wraw + p, P);
+    Traj<HT> u;
+    init_start<HT>(k, s, a.cur_speed ? a.cur_speed[b] : v0, u);
+    const float loss = solve_start<HT, NOT_, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+    m.loss[s * P + p] = loss;
+    if (live) {
+        a.losses[(size_t)s * B + b] = loss;
+        if (a.all_plans) {
+            const int H = HT > 0 ? HT : k.H;
+#pragma unroll
+            for (int t = 0; t < Traj<HT>::HM; ++t)
+                if (t < H) {
+                    a.all_plans[((size_t)(s * H + t) * 2 + 0) * B + b] = u.ua[t];
+                    a.all_plans[((size_t)(s * H + t) * 2 + 1) * B + b] = u.uw[t];
+                }
+        }
+    }
+    __syncthreads();
+    // losses.index(min(losses)): first strict minimum (naive_planner.py:161-164)
+    int bi = 0;
+    float bl = m.loss[p];
+    for (int q = 1; q < k.S; ++q) {
+        const float l = m.loss[q * P + p];
+        if (l < bl) { bl = l; bi = q; }
+    }
+    if (live && s == bi) {
+        const int H = HT > 0 ? HT : k.H;
+        a.best[b] = bi;
+#pragma unroll
+        for (int t = 0; t < Traj<HT>::HM; ++t)
+            if (t < H) {
+                a.plan[(size_t)(t * 2 + 0) * B + b] = u.ua[t];
+                a.plan[(size_t)(t * 2 + 1) * B + b] = u.uw[t];
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_episode
+// ---------------------------------------------------------------------------------------------
+template <int HT, int NOT_, bool PRECISE>
+__global__ void __launch_bounds__(kMaxThreads)
+k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
+    extern __shared__ float smem_raw[];
+    const int P = a.P;
+    const Smem m = carve(smem_raw, k, P, true);
+    const int p = threadIdx.x % P, s = threadIdx.x / P;
+    const long long b_raw = (long long)blockIdx.x * P + p;
+    const bool live = b_raw < a.B;
+    const long long b = live ? b_raw : a.B - 1;
+    const long long B = a.B;
+    const int C = k.NO + 1;
+
+    if (threadIdx.x < k.K) m.wtrue[threadIdx.x] = a.true_weights[threadIdx.x];
+    int unlucky = 0;
+    if (s == 0) {
+        const long long wc = weight_column(a.weight_idx, a.Bw, b);
+        for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.plan_weights[(size_t)i * a.Bw + wc];
+        for (int c = 0; c < 4; ++c) m.world[c * P + p] = a.robot_init[(size_t)c * B + b];
+        for (int j = 0; j < k.NO; ++j)
+            for (int c = 0; c < 4; ++c)
+                m.world[((j + 1) * 4 + c) * P + p] =
+                    a.other_init ? a.other_init[(size_t)(j * 4 + c) * B + b] : sc.init_state[j][c];
+        if (a.unlucky_idx) unlucky = a.unlucky_idx[b];
+    }
+    __syncthreads();
+    const GradW gw = make_gradw(k, m.wraw + p, P);
+    float ret = 0.0f;
+
+    for (int i = 0; i < a.T; ++i) {
+        const int ti = a.t0 + i;
+        if (s == 0) {
+            // ReplanningCarWorld.step: teleport before anything else (replanning_world.py:31-34)
+            if (sc.critical_t > 0 && ti + 1 == sc.critical_t && unlucky >= 1 && unlucky < C)
+                for (int c = 0; c < 4; ++c) m.world[(unlucky * 4 + c) * P + p] = sc.teleport_state[c];
+            if (a.traj_states && live)
+                for (int c = 0; c < C * 4; ++c)
+                    a.traj_states[((size_t)i * C * 4 + c) * B + b] = m.world[c * P + p];
+            // true-weight reward of the past state (mpc_ord.py:96-99)
+            {
+                const float x = m.world[p], y = m.world[P + p], v = m.world[2 * P + p], th = m.world[3 * P + p];
+                float sn, cs;
+                Mth<PRECISE>::sincos_(th, sn, cs);
+                ret = __fadd_rn(ret, reward_value<PRECISE>(k, m.wtrue, 1, x, y, v, sn, m.world + 4 * P + p,
+                                                           4 * P, P));
+            }
+            // what the planner assumes about the other cars (planner_car.py:58-80, naive_planner.py:47-67)
+            for (int j = 0; j < k.NO; ++j) {
+                const float *w = m.world + (size_t)(j + 1) * 4 * P + p;
+                float x = w[0], y = w[P], v = w[2 * P], th = w[3 * P];
+                for (int t = 0; t < k.H; ++t) {
+                    float oa = 0.0f, oo = 0.0f;
+                    if (k.other_mode == 1 && sc.kind[j] == 1) {   // plan replayed from index 0 (quirk Q4)
+                        const bool in_plan = t < sc.plan_len[j];
+                        oa = in_plan ? sc.plan[j][t][0] : sc.control[j][0];
+                        oo = in_plan ? sc.plan[j][t][1] : sc.control[j][1];
+                    }
+                    other_model_step<PRECISE>(x, y, v, th, k.other_mode == 1, oa, oo, k.dt, k.dt2);
+                    m.oth[(size_t)((t * k.NO + j) * 2 + 0) * P + p] = x;
+                    m.oth[(size_t)((t * k.NO + j) * 2 + 1) * P + p] = y;
+                }
+            }
+        }
+        __syncthreads();
+
+        const float x0 = m.world[p], y0 = m.world[P + p], v0 = m.world[2 * P + p], th0 = m.world[3 * P + p];
+        Traj<HT> u;
+        init_start<HT>(k, s, v0, u);
+        const float loss = solve_start<HT, NOT_, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+        m.loss[s * P + p] = loss;
+        m.u0[(s * 2 + 0) * P + p] = u.ua[0];
+        m.u0[(s * 2 + 1) * P + p] = u.uw[0];
+        __syncthreads();
+
+        if (s == 0) {
+            int bi = 0;
+            float bl = m.loss[p];
+            for (int q = 1; q < k.S; ++q) {
+                const float l = m.loss[q * P + p];
+                if (l < bl) { bl = l; bi = q; }
+            }
+            const float ua = m.u0[(bi * 2 + 0) * P + p], uw = m.u0[(bi * 2 + 1) * P + p];
+            if (live) {
+                if (a.traj_controls) {
+                    a.traj_controls[((size_t)i * 2 + 0) * B + b] = ua;
+                    a.traj_controls[((size_t)i * 2 + 1) * B + b] = uw;
+                }
+                if (a.traj_best) a.traj_best[(size_t)i * B + b] = bi;
+            }
+            // CarWorld.step second phase: every car integrates (world.py:106-107, car.py:87)
+            {
+                float x = x0, y = y0, v = v0, th = th0;
+                dynamics_step<PRECISE>(x, y, v, th, ua, uw, k.dt, k.dt2, k.mu);
+                m.world[p] = x; m.world[P + p] = y; m.world[2 * P + p] = v; m.world[3 * P + p] = th;
+            }
+            for (int j = 0; j < k.NO; ++j) {
+                float *w = m.world + (size_t)(j + 1) * 4 * P + p;
+                float x = w[0], y = w[P], v = w[2 * P], th = w[3 * P];
+                const bool in_plan = sc.kind[j] == 1 && ti < sc.plan_len[j];   // fixed_plan_car.py:25-31
+                const float oa = in_plan ? sc.plan[j][ti][0] : sc.control[j][0];
+                const float oo = in_plan ? sc.plan[j][ti][1] : sc.control[j][1];
+                dynamics_step<PRECISE>(x, y, v, th, oa, oo, k.dt, k.dt2, sc.friction[j]);
+                w[0] = x; w[P] = y; w[2 * P] = v; w[3 * P] = th;
+            }
+        }
+        __syncthreads();
+    }
+    if (s == 0 && live) {
+        a.returns[b] = ret;
+        if (a.final_world)
+            for (int c = 0; c < C * 4; ++c) a.final_world[(size_t)c * B + b] = m.world[c * P + p];
+    }
+}
+
+inline int cuda_status() { return cudaGetLastError() == cudaSuccess ? OCD_OK : OCD_ECUDA; }
+
+template <typename KernelT>
+inline int prepare_smem(KernelT kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (bytes > 227 * 1024) return OCD_EUNSUP;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return OCD_ECUDA;
+    }
+    return OCD_OK;
+}
+
+template <int HT, int NOT_, bool PRECISE>
+int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false) * sizeof(float);
+    auto kern = k_solve<HT, NOT_, PRECISE>;
+    int rc = prepare_smem(kern, bytes);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
+    kern<<<grid, k.S * a.P, bytes, st>>>(k, a);
+    return cuda_status();
+}
+
+template <int HT, int NOT_, bool PRECISE>
+int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs &a, cudaStream_t st) {
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true) * sizeof(float);
+    auto kern = k_episode<HT, NOT_, PRECISE>;
+    int rc = prepare_smem(kern, bytes);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
+    kern<<<grid, k.S * a.P, bytes, st>>>(k, sc, a);
+    return cuda_status();
+}
+
+}  // namespace ocd
