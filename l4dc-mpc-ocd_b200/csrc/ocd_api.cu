@@ -15,19 +15,17 @@
 namespace ocd {
 
 // specialisations built by ocd_inst.cu
-#define OCD_EXTERN(HT, NO)                                                                                   \
-    extern template int launch_solve_t<HT, NO, false>(const KParams &, const SolveArgs &, cudaStream_t);     \
-    extern template int launch_solve_t<HT, NO, true>(const KParams &, const SolveArgs &, cudaStream_t);      \
-    extern template int launch_episode_t<HT, NO, false>(const KParams &, const ocd_scenario &,               \
-                                                        const EpisodeArgs &, cudaStream_t);                  \
-    extern template int launch_episode_t<HT, NO, true>(const KParams &, const ocd_scenario &,                \
-                                                       const EpisodeArgs &, cudaStream_t);
-OCD_EXTERN(5, 1)
-OCD_EXTERN(5, 2)
-OCD_EXTERN(5, 0)
-OCD_EXTERN(6, 1)
-OCD_EXTERN(3, 0)
-OCD_EXTERN(0, 0)
+#define OCD_EXTERN(HT, NO, LT)                                                                               \
+    extern template int launch_solve_t<HT, NO, LT, false>(const KParams &, const SolveArgs &, cudaStream_t); \
+    extern template int launch_solve_t<HT, NO, LT, true>(const KParams &, const SolveArgs &, cudaStream_t);  \
+    extern template int launch_episode_t<HT, NO, LT, false>(const KParams &, const ocd_scenario &,           \
+                                                            const EpisodeArgs &, cudaStream_t);              \
+    extern template int launch_episode_t<HT, NO, LT, true>(const KParams &, const ocd_scenario &,            \
+                                                           const EpisodeArgs &, cudaStream_t);
+OCD_EXTERN(5, 1, 3)   // finite_horizon, local_opt, the bench shape
+OCD_EXTERN(5, 2, 2)   // replanning
+OCD_EXTERN(6, 1, 3)   // finite_horizon validation (H=6, n_iter=200)
+OCD_EXTERN(0, 0, 0)   // any other shape: runtime H, cars, lanes
 #undef OCD_EXTERN
 
 // ---------------------------------------------------------------------------------------------
@@ -39,8 +37,9 @@ k_reward_grad(const __grid_constant__ KParams k, const float *world, const float
               const float *other_controls, long long Bo, const float *weights, long long Bw,
               const int32_t *weight_idx, float *reward, float *grad, long long B) {
     // one thread per problem; its slab column lives in local memory (runtime H, runtime NO)
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b_raw < B;
+    const long long b = live ? b_raw : B - 1;     // whole warps stay converged: feature_grad votes
     float oth[OCD_MAX_H * OCD_MAX_OTHER * 2];
     // weights are read straight from global memory (element stride Bw).  A thread-local copy
     // here was miscompiled by nvcc 12.9: the copy's stack slot was reused for reward_value's
@@ -63,14 +62,15 @@ k_reward_grad(const __grid_constant__ KParams k, const float *world, const float
         u.ua[t] = controls[(size_t)(t * 2 + 0) * B + b];
         u.uw[t] = controls[(size_t)(t * 2 + 1) * B + b];
     }
-    reward[b] = rollout_reward<0, PRECISE>(k, w, ws, x0, y0, v0, th0, oth, 1, u);
+    const float R = rollout_reward<0, 0, PRECISE>(k, w, ws, x0, y0, v0, th0, oth, 1, u);
+    if (live) reward[b] = R;
     if (grad) {
-        const GradW gw = make_gradw(k, w, ws);
+        const GradW gw = make_gradw<0>(k, w, ws);
         float ga[OCD_MAX_H], go[OCD_MAX_H];
         float sn0, cs0;
         Mth<PRECISE>::sincos_(th0, sn0, cs0);
-        sgd_iteration<0, 0, PRECISE, false>(k, gw, x0, y0, v0, th0, sn0, cs0, oth, 1, u, ga, go);
-        for (int t = 0; t < k.H; ++t) {
+        sgd_iteration<0, 0, 0, PRECISE, false>(k, gw, x0, y0, v0, th0, sn0, cs0, oth, 1, u, ga, go);
+        for (int t = 0; t < k.H && live; ++t) {
             grad[(size_t)(t * 2 + 0) * B + b] = ga[t];
             grad[(size_t)(t * 2 + 1) * B + b] = go[t];
         }
@@ -85,7 +85,7 @@ k_features(const __grid_constant__ KParams k, const float *world, float *phi, lo
     float sn, cs;
     Mth<PRECISE>::sincos_(world[3 * B + b], sn, cs);
     float f[OCD_MAX_LANES + 4];
-    feature_values<PRECISE>(k, world[b], world[B + b], world[2 * B + b], sn, world + 4 * B + b,
+    feature_values<0, PRECISE, false>(k, world[b], world[B + b], world[2 * B + b], sn, world + 4 * B + b,
                             (int)(4 * B), (int)B, f);
 #pragma unroll
     for (int i = 0; i < OCD_MAX_LANES + 4; ++i)
@@ -165,18 +165,14 @@ static int pick_P(long long B) {
     return B >= 64LL * 148 * 4 ? 64 : 32;
 }
 
-// (H, NO) specialisations: the shipped scenarios (H=5/6, one or two other cars), the planner
-// known-answer test (H=3) and a runtime-shape fallback.
-#define OCD_DISPATCH(FN, PRECISE, ...)                                                  \
-    do {                                                                                \
-        const int no = k.NO <= 2 ? k.NO : 0;                                            \
-        const int h = (k.H == 3 || k.H == 5 || (k.H == 6 && no == 1)) ? k.H : 0;        \
-        if (h == 5 && no == 1) return FN<5, 1, PRECISE>(__VA_ARGS__);                   \
-        if (h == 5 && no == 2) return FN<5, 2, PRECISE>(__VA_ARGS__);                   \
-        if (h == 5) return FN<5, 0, PRECISE>(__VA_ARGS__);                              \
-        if (h == 6 && no == 1) return FN<6, 1, PRECISE>(__VA_ARGS__);                   \
-        if (h == 3) return FN<3, 0, PRECISE>(__VA_ARGS__);                              \
-        return FN<0, 0, PRECISE>(__VA_ARGS__);                                          \
+// (H, other cars, lanes) specialisations: the shipped scenarios; everything else takes the
+// runtime-shape kernels.
+#define OCD_DISPATCH(FN, PRECISE, ...)                                                      \
+    do {                                                                                    \
+        if (k.H == 5 && k.NO == 1 && k.L == 3) return FN<5, 1, 3, PRECISE>(__VA_ARGS__);    \
+        if (k.H == 5 && k.NO == 2 && k.L == 2) return FN<5, 2, 2, PRECISE>(__VA_ARGS__);    \
+        if (k.H == 6 && k.NO == 1 && k.L == 3) return FN<6, 1, 3, PRECISE>(__VA_ARGS__);    \
+        return FN<0, 0, 0, PRECISE>(__VA_ARGS__);                                           \
     } while (0)
 
 static int launch_solve(const KParams &k, bool precise, const SolveArgs &a, cudaStream_t st) {

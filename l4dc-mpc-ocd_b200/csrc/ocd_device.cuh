@@ -16,6 +16,12 @@
 //   rollout + SGD       interact_drive/planner/naive_planner.py:32-79, 107-164
 // Gradient conventions are TensorFlow 2.1's: clip masks inclusive, Minimum
 // passes on <=, reduce_min/max split evenly among ties, where() blocks the unselected branch.
+//
+// Two math back-ends share every formula:
+//   PRECISE  libdevice sinf/cosf/expf, IEEE division, reference op order where it matters.
+//   FAST     one MUFU op per transcendental (sin/cos/ex2/rcp .approx), branch-free collision
+//            bump, constants folded into the weights.  The hot loop is issue-bound, so FAST is
+//            written to minimise the instruction count per (iteration x horizon step).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,9 +42,16 @@ struct KParams {
     float lane_x[OCD_MAX_LANES];
 };
 
+// collision bump half-widths (merging.py:70-73) and their reciprocals
+#define OCD_BUMP_HX 0.08f
+#define OCD_BUMP_HY 0.15f
+#define OCD_BUMP_IX 12.5f
+#define OCD_BUMP_IY 6.6666667f
+#define OCD_LOG2E   1.4426950408889634f
+#define OCD_FULL    0xffffffffu
+
 // ---------------------------------------------------------------------------------------------
-// Math back-ends.  FAST: one MUFU op per transcendental (sin/cos/ex2/rcp .approx).  PRECISE:
-// libdevice sinf/cosf/expf and IEEE division, op order as in the reference.
+// Math back-ends.
 // ---------------------------------------------------------------------------------------------
 template <bool PRECISE>
 struct Mth;
@@ -54,11 +67,12 @@ struct Mth<false> {
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
-    static __device__ __forceinline__ float exp_(float x) {   // e^x
+    static __device__ __forceinline__ float ex2_(float x) {   // 2^x
         float r;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
+    static __device__ __forceinline__ float exp_(float x) { return ex2_(x * OCD_LOG2E); }
     static __device__ __forceinline__ float div_(float a, float b) { return a * rcp_(b); }
 };
 
@@ -72,6 +86,13 @@ struct Mth<true> {
     static __device__ __forceinline__ float exp_(float x) { return expf(x); }
     static __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 };
+
+// Other cars' positions are kept in a per-block slab.  PRECISE stores them raw; FAST stores them
+// already divided by the bump half-width, so that the normalised offset is one FFMA.
+template <bool PRECISE>
+__device__ __forceinline__ float slab_x(float ox) { return PRECISE ? ox : ox * OCD_BUMP_IX; }
+template <bool PRECISE>
+__device__ __forceinline__ float slab_y(float oy) { return PRECISE ? oy : oy * OCD_BUMP_IY; }
 
 // ---------------------------------------------------------------------------------------------
 // a1  car_dynamics_step (simulation_utils.py:9-21), one car.
@@ -121,89 +142,139 @@ __device__ __forceinline__ void other_model_step(float &x, float &y, float &v, f
 // ---------------------------------------------------------------------------------------------
 // Smooth helpers (math_utils.py).  Each returns the value and its derivative.
 // ---------------------------------------------------------------------------------------------
-// smooth_bump(c - hw, c + hw)(z): value b and db/dz.  FAST uses c and 1/hw directly; PRECISE
-// recomputes width and center from start/end in float32 like math_utils.py:169-171.
+// smooth_bump(c - hw, c + hw)(z) as a function of the normalised offset n = (z - c)/hw:
+// value b and db/dn.
 template <bool PRECISE>
-__device__ __forceinline__ void bump_vg(float z, float c, float hw, float inv_hw, float &b, float &db) {
-    float n, iw;
+__device__ __forceinline__ void bump_n(float n, float &b, float &dbdn) {
+    const float om = fmaf(-n, n, 1.0f);
+    b = 0.0f;
+    dbdn = 0.0f;
+    if (n * n < 1.0f) {
+        const float r = Mth<PRECISE>::rcp_(om);
+        b = Mth<PRECISE>::exp_(1.0f - r);
+        dbdn = b * (-2.0f * n) * (r * r);
+    }
+}
+
+// Normalised offset of z from a slab coordinate.  PRECISE recomputes width and center from
+// start/end in float32 like math_utils.py:169-171; FAST is one FFMA on the pre-scaled centre.
+template <bool PRECISE, bool SCALED>
+__device__ __forceinline__ float bump_offset(float z, float c, float hw, float inv_hw, float &inv_w) {
     if (PRECISE) {
         const float start = __fsub_rn(c, hw), end = __fadd_rn(c, hw);
         const float width = __fmul_rn(__fsub_rn(end, start), 0.5f);
         const float center = __fmul_rn(__fadd_rn(start, end), 0.5f);
-        n = __fdiv_rn(__fsub_rn(z, center), width);
-        iw = __fdiv_rn(1.0f, width);
-    } else {
-        n = (z - c) * inv_hw;
-        iw = inv_hw;
+        inv_w = __fdiv_rn(1.0f, width);
+        return __fdiv_rn(__fsub_rn(z, center), width);
     }
-    const float om = fmaf(-n, n, 1.0f);
-    b = 0.0f;
-    db = 0.0f;
-    if (n * n < 1.0f) {
-        const float r = Mth<PRECISE>::rcp_(om);
-        b = Mth<PRECISE>::exp_(1.0f - r);
-        db = b * (-2.0f * n) * (r * r) * iw;
-    }
+    inv_w = inv_hw;
+    return SCALED ? fmaf(z, inv_hw, -c) : (z - c) * inv_hw;
 }
 
 // fence(x) = (T(x) + T(-x)) * |x| with T = smooth_threshold(0.05*num_lanes, 0.05)
 // (merging.py:80-81).  T(-|x|) is identically 0 (its _f argument is <= 0), so the feature is
 // T(|x|)*|x|: 0 below the ramp, |x| above it, two exponentials only inside the ramp.
+// Precondition for the caller: q = |x| - thr_lo > 0.
+template <bool PRECISE>
+__device__ __forceinline__ void fence_inside(const KParams &k, float x, float ax, float q, float &f, float &df) {
+    const float u2 = k.thr_w - q;
+    if (u2 > 0.0f) {
+        const float r1 = Mth<PRECISE>::rcp_(k.fshape * q);
+        const float r2 = Mth<PRECISE>::rcp_(k.fshape * u2);
+        const float F1 = Mth<PRECISE>::exp_(-r1);
+        const float F2 = Mth<PRECISE>::exp_(-r2);
+        const float inv = Mth<PRECISE>::rcp_(F1 + F2);
+        const float T = F1 * inv;
+        // F'(q) = F(q)/(shape q^2) = F * shape * r^2
+        const float dT = (F1 * F2) * (k.fshape * fmaf(r1, r1, r2 * r2)) * (inv * inv);
+        f = T * ax;
+        df = copysignf(fmaf(dT, ax, T), x);
+    } else {
+        f = ax;
+        df = copysignf(1.0f, x);
+    }
+}
+
 template <bool PRECISE>
 __device__ __forceinline__ void fence_vg(const KParams &k, float x, float &f, float &df) {
     const float ax = fabsf(x);
     const float q = ax - k.thr_lo;
-    const float u2 = k.thr_w - q;
-    const float sg = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
     f = 0.0f;
     df = 0.0f;
-    if (q > 0.0f) {
-        if (u2 > 0.0f) {
-            const float r1 = Mth<PRECISE>::rcp_(k.fshape * q);
-            const float r2 = Mth<PRECISE>::rcp_(k.fshape * u2);
-            const float F1 = Mth<PRECISE>::exp_(-r1);
-            const float F2 = Mth<PRECISE>::exp_(-r2);
-            const float inv = Mth<PRECISE>::rcp_(F1 + F2);
-            const float T = F1 * inv;
-            // F'(q) = F(q)/(shape q^2) = F * shape * r^2
-            const float dT = (F1 * F2) * (k.fshape * fmaf(r1, r1, r2 * r2)) * (inv * inv);
-            f = T * ax;
-            df = sg * fmaf(dT, ax, T);
-        } else {
-            f = ax;
-            df = sg;
-        }
-    }
+    if (q > 0.0f) fence_inside<PRECISE>(k, x, ax, q, f, df);
 }
 
 // Per-problem weights, pre-combined for the gradient:
-//   sum_i w_i * d/dx[10 (x-l_i)^2] = GA*x + GB ;  w0x2 = 2 w_speed ; wmin20 = 20 w_min
+//   sum_i w_i * d/dx[10 (x-l_i)^2] = GA*x + GB ;  w0x2 = 2 w_speed ; wmin20 = 20 w_min ;
+//   wcx / wcy = collision weight times the bump's d n / d position and the -2 of bump'.
 struct GradW {
-    float w0x2, GA, GB, wmin20, wcol, wfence;
+    float w0x2, GA, GB, wmin20, wcol, wfence, wcx, wcy;
 };
 
+template <int LT>
 __device__ __forceinline__ GradW make_gradw(const KParams &k, const float *w /*[K] stride ws*/, int ws) {
+    const int L = LT > 0 ? LT : k.L;
     GradW g;
     g.w0x2 = 2.0f * w[0];
     float sa = 0.0f, sb = 0.0f;
 #pragma unroll
-    for (int i = 0; i < OCD_MAX_LANES; ++i)
-        if (i < k.L) {
+    for (int i = 0; i < (LT > 0 ? LT : OCD_MAX_LANES); ++i)
+        if (i < L) {
             const float wi = w[(1 + i) * ws];
             sa += wi;
             sb = fmaf(wi, k.lane_x[i], sb);
         }
     g.GA = 20.0f * sa;
     g.GB = -20.0f * sb;
-    g.wmin20 = 20.0f * w[(1 + k.L) * ws];
-    g.wcol = w[(2 + k.L) * ws];
-    g.wfence = w[(3 + k.L) * ws];
+    g.wmin20 = 20.0f * w[(1 + L) * ws];
+    g.wcol = w[(2 + L) * ws];
+    g.wfence = w[(3 + L) * ws];
+    g.wcx = g.wcol * (-2.0f * OCD_BUMP_IX);
+    g.wcy = g.wcol * (-2.0f * OCD_BUMP_IY);
+    // keep the combined constants in registers: without the barrier ptxas rematerialises GA/GB from
+    // the raw weights inside the hot loop (4 extra instructions per horizon step)
+    asm volatile("" : "+f"(g.GA), "+f"(g.GB), "+f"(g.wmin20), "+f"(g.w0x2));
+    asm volatile("" : "+f"(g.wcx), "+f"(g.wcy), "+f"(g.wfence), "+f"(g.wcol));
     return g;
 }
 
+// d/dx of min_i 10 (x - l_i)^2, divided by 20: the offset to the nearest lane, averaged over
+// exact ties (TF reduce_min splits the gradient evenly).  Ties are found on the feature values
+// themselves, as the reference does; the averaging runs only when one occurred.
+template <int LT, bool PRECISE>
+__device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
+    const int L = LT > 0 ? LT : k.L;
+    float dsel = x - k.lane_x[0];
+    float fm = (dsel * dsel) * 10.0f;
+    bool tie = false;
+#pragma unroll
+    for (int i = 1; i < (LT > 0 ? LT : OCD_MAX_LANES); ++i)
+        if (i < L) {
+            const float d = x - k.lane_x[i];
+            const float f = (d * d) * 10.0f;
+            tie = tie || (f == fm);
+            dsel = (f < fm) ? d : dsel;
+            fm = fminf(fm, f);
+        }
+    // rare: an earlier tie may have been beaten later, so recount against the minimum.  FAST asks
+    // the whole warp first, so that the common case is one uniform branch.
+    if (PRECISE ? tie : __any_sync(OCD_FULL, tie)) {
+        float sum = 0.0f, cnt = 0.0f;
+        for (int i = 0; i < L; ++i) {
+            const float d = x - k.lane_x[i];
+            if ((d * d) * 10.0f == fm) {
+                sum += d;
+                cnt += 1.0f;
+            }
+        }
+        dsel = (tie && cnt > 1.0f) ? __fdiv_rn(sum, cnt) : dsel;
+    }
+    return dsel;
+}
+
 // Gradient of w.phi with respect to the robot state (x, y, v, th) at one world state.
-//   oth: other cars' positions, x of car j at oth[j*jstride], y at oth[j*jstride + cstride].
-template <int NOT_, bool PRECISE>
+//   oth: other cars' slab coordinates, x of car j at oth[j*jstride], y at oth[j*jstride + cstride].
+template <int NOT_, int LT, bool PRECISE>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
                                              float &gx, float &gy, float &gv, float &gth) {
@@ -213,83 +284,95 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         const float e = fmaf(v, sn, -k.ts);
         const float ke = (e * e <= k.bound) ? (w.w0x2 * e) : 0.0f;
         gv = ke * sn;
-        gth = ke * v * cs;
+        gth = (ke * v) * cs;
     }
     // lanes: sum_i w_i 10 (x - l_i)^2 and the min over lanes                 merging.py:61-65
-    gx = fmaf(w.GA, x, w.GB);
-    {
-        float fbest = 0.0f, sum = 0.0f, cnt = 1.0f;
-#pragma unroll
-        for (int i = 0; i < OCD_MAX_LANES; ++i)
-            if (i < k.L) {
-                const float dx = x - k.lane_x[i];
-                const float f = (dx * dx) * 10.0f;
-                if (i == 0 || f < fbest) {
-                    fbest = f; sum = dx; cnt = 1.0f;
-                } else if (f == fbest) {
-                    sum += dx; cnt += 1.0f;
-                }
-            }
-        if (cnt != 1.0f) sum = __fdiv_rn(sum, cnt);
-        gx = fmaf(w.wmin20, sum, gx);
-    }
+    gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE>(k, x), fmaf(w.GA, x, w.GB));
     // collision: max_j bump_x * bump_y                                        merging.py:67-78
-    {
+    if (PRECISE) {
         float best = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
 #pragma unroll(NOT_ > 0 ? NOT_ : 1)
         for (int j = 0; j < NO; ++j) {
-                const float ox = oth[j * jstride], oy = oth[j * jstride + cstride];
-                float val = 0.0f, vx = 0.0f, vy = 0.0f;
-                if (PRECISE) {
-                    float bx, dbx, by, dby;
-                    bump_vg<true>(x, ox, 0.08f, 12.5f, bx, dbx);
-                    bump_vg<true>(y, oy, 0.15f, 6.6666667f, by, dby);
-                    val = bx * by; vx = dbx * by; vy = bx * dby;
-                } else {
-                    // both bumps share one exponential: bx*by = exp(2 - 1/(1-nx^2) - 1/(1-ny^2))
-                    const float nx = (x - ox) * 12.5f, ny = (y - oy) * 6.6666667f;
-                    const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
-                    if (ux > 0.0f && uy > 0.0f) {
-                        const float rx = Mth<false>::rcp_(ux), ry = Mth<false>::rcp_(uy);
-                        val = Mth<false>::exp_(2.0f - rx - ry);
-                        vx = val * (-25.0f * nx) * (rx * rx);          // -2 n r^2 / 0.08
-                        vy = val * (-13.333333f * ny) * (ry * ry);     // -2 n r^2 / 0.15
-                    }
-                }
-                if (j == 0 || val > best) {
-                    best = val; sx = vx; sy = vy; cnt = 1.0f;
-                } else if (val == best) {
-                    sx += vx; sy += vy; cnt += 1.0f;
-                }
+            float iwx, iwy, bx, dbx, by, dby;
+            const float nx = bump_offset<true, false>(x, oth[j * jstride], OCD_BUMP_HX, OCD_BUMP_IX, iwx);
+            const float ny = bump_offset<true, false>(y, oth[j * jstride + cstride], OCD_BUMP_HY, OCD_BUMP_IY, iwy);
+            bump_n<true>(nx, bx, dbx);
+            bump_n<true>(ny, by, dby);
+            const float val = bx * by, vx = (dbx * iwx) * by, vy = bx * (dby * iwy);
+            if (j == 0 || val > best) {
+                best = val; sx = vx; sy = vy; cnt = 1.0f;
+            } else if (val == best) {
+                sx += vx; sy += vy; cnt += 1.0f;
             }
+        }
         if (cnt != 1.0f) {
             sx = __fdiv_rn(sx, cnt);
             sy = __fdiv_rn(sy, cnt);
         }
         gx = fmaf(w.wcol, sx, gx);
         gy = w.wcol * sy;
+    } else {
+        // Both bumps share one exponential: bx*by = exp(2 - 1/(1-nx^2) - 1/(1-ny^2)).  Outside
+        // the support 1-n^2 is clamped to a tiny positive number: the exponential underflows to
+        // exactly 0 and takes every derivative with it, so no branch and no select is needed.
+        // hx, hy below are d(val)/d(position) without the constant -2/half-width (folded into
+        // wcx, wcy).  A warp with every lane outside every support skips the transcendental part.
+        float best = 0.0f, hx = 0.0f, hy = 0.0f, cnt = 1.0f;
+#pragma unroll(NOT_ > 0 ? NOT_ : 1)
+        for (int j = 0; j < NO; ++j) {
+            const float nx = fmaf(x, OCD_BUMP_IX, -oth[j * jstride]);
+            const float ny = fmaf(y, OCD_BUMP_IY, -oth[j * jstride + cstride]);
+            const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
+            float val = 0.0f, vx = 0.0f, vy = 0.0f;
+            if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
+                const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
+                val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
+                vx = (val * nx) * (rx * rx);
+                vy = (val * ny) * (ry * ry);
+            }
+            if (NOT_ == 1) {
+                hx = vx; hy = vy;
+            } else if (j == 0 || val > best) {
+                best = val; hx = vx; hy = vy; cnt = 1.0f;
+            } else if (val == best) {
+                hx += vx; hy += vy; cnt += 1.0f;
+            }
+        }
+        if (NOT_ != 1 && cnt != 1.0f) {
+            const float r = __fdiv_rn(1.0f, cnt);
+            hx *= r;
+            hy *= r;
+        }
+        gx = fmaf(w.wcx, hx, gx);
+        gy = w.wcy * hy;
     }
     // fence                                                                    merging.py:80-81
     {
-        float f, df;
-        fence_vg<PRECISE>(k, x, f, df);
-        gx = fmaf(w.wfence, df, gx);
+        const float ax = fabsf(x);
+        const float q = ax - k.thr_lo;
+        if (PRECISE ? (q > 0.0f) : __any_sync(OCD_FULL, q > 0.0f)) {
+            float f = 0.0f, df = 0.0f;
+            if (q > 0.0f) fence_inside<PRECISE>(k, x, ax, q, f, df);
+            gx = fmaf(w.wfence, df, gx);
+        }
     }
 }
 
 // Feature vector phi[K] at one world state, in the reference's order and op order.
-template <bool PRECISE>
+// SCALED: the other cars' coordinates come from a FAST slab (already divided by the half-width).
+template <int LT, bool PRECISE, bool SCALED>
 __device__ __forceinline__ void feature_values(const KParams &k, float x, float y, float v, float sn,
                                                const float *oth, int jstride, int cstride,
                                                float (&phi)[OCD_MAX_LANES + 4]) {
+    const int L = LT > 0 ? LT : k.L;
     {
         const float e = __fsub_rn(__fmul_rn(v, sn), k.ts);
         phi[0] = fminf(__fmul_rn(e, e), k.bound);
     }
     float fmin_ = 0.0f;
 #pragma unroll
-    for (int i = 0; i < OCD_MAX_LANES; ++i)
-        if (i < k.L) {
+    for (int i = 0; i < (LT > 0 ? LT : OCD_MAX_LANES); ++i)
+        if (i < L) {
             const float dx = x - k.lane_x[i];
             const float f = __fmul_rn(__fmul_rn(dx, dx), 10.0f);
             phi[1 + i] = f;
@@ -297,10 +380,10 @@ __device__ __forceinline__ void feature_values(const KParams &k, float x, float 
         }
     float best = 0.0f;
     for (int j = 0; j < k.NO; ++j) {
-        const float ox = oth[j * jstride], oy = oth[j * jstride + cstride];
-        float bx, dbx, by, dby;
-        bump_vg<PRECISE>(x, ox, 0.08f, 12.5f, bx, dbx);
-        bump_vg<PRECISE>(y, oy, 0.15f, 6.6666667f, by, dby);
+        float iw, bx, dbx, by, dby;
+        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(x, oth[j * jstride], OCD_BUMP_HX, OCD_BUMP_IX, iw), bx, dbx);
+        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(y, oth[j * jstride + cstride], OCD_BUMP_HY, OCD_BUMP_IY, iw),
+                        by, dby);
         const float val = __fmul_rn(bx, by);
         best = (j == 0) ? val : fmaxf(best, val);
     }
@@ -309,7 +392,7 @@ __device__ __forceinline__ void feature_values(const KParams &k, float x, float 
     // write the tail with static indices only (phi stays in registers)
 #pragma unroll
     for (int i = 1; i <= OCD_MAX_LANES; ++i)
-        if (i == k.L) {
+        if (i == L) {
             phi[1 + i] = fmin_;
             if (i + 2 < OCD_MAX_LANES + 4) phi[2 + i] = best;
             if (i + 3 < OCD_MAX_LANES + 4) phi[3 + i] = fen;
@@ -317,11 +400,11 @@ __device__ __forceinline__ void feature_values(const KParams &k, float x, float 
 }
 
 // w . phi summed in feature order (linear_reward_car.py:53).  w[k] at w[k*ws].
-template <bool PRECISE>
+template <int LT, bool PRECISE, bool SCALED>
 __device__ __forceinline__ float reward_value(const KParams &k, const float *w, int ws, float x, float y,
                                               float v, float sn, const float *oth, int jstride, int cstride) {
     float phi[OCD_MAX_LANES + 4];
-    feature_values<PRECISE>(k, x, y, v, sn, oth, jstride, cstride, phi);
+    feature_values<LT, PRECISE, SCALED>(k, x, y, v, sn, oth, jstride, cstride, phi);
     float r = 0.0f;
 #pragma unroll
     for (int i = 0; i < OCD_MAX_LANES + 4; ++i)
@@ -334,7 +417,7 @@ __device__ __forceinline__ float reward_value(const KParams &k, const float *w, 
 //   HT > 0: horizon known at compile time, everything unrolled into registers.
 //   HT == 0: runtime horizon (<= OCD_MAX_H), per-step arrays in local memory.
 // `oth` points at this problem's column of the block's other-car slab laid out
-// [H][NO][2][P]: position c of car j at step t is oth[((t*NO + j)*2 + c)*P].
+// [H][NO][2][P]: coordinate c of car j at step t is oth[((t*NO + j)*2 + c)*P].
 // ---------------------------------------------------------------------------------------------
 template <int HT>
 struct Traj {
@@ -342,7 +425,7 @@ struct Traj {
     float ua[HM], uw[HM];                      // controls (acceleration, angular velocity)
 };
 
-template <int HT, int NOT_, bool PRECISE, bool UPDATE>
+template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE>
 __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                               float th0, float sn0, float cs0, const float *oth, int P,
                                               Traj<HT> &u, float *ga_out, float *gw_out) {
@@ -354,36 +437,40 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
     float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
-            const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
-            const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
-            const float total = fmaf(-k.mu, v * v, ac);
-            const float dist = fmaf(total, k.hdt2, v * k.dt);
-            sv[t] = v; sc[t] = cs; ss[t] = sn; sd[t] = dist;
-            x = fmaf(cs, dist, x);
-            y = fmaf(sn, dist, y);
-            v = fmaf(total, k.dt, v);
-            th = fmaf(oc, k.dt, th);
-            Mth<PRECISE>::sincos_(th, sn, cs);
-            feature_grad<NOT_, PRECISE>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
+        const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
+        const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
+        const float total = fmaf(-k.mu, v * v, ac);
+        const float dist = fmaf(total, k.hdt2, v * k.dt);
+        sv[t] = v; sc[t] = cs; ss[t] = sn; sd[t] = dist;
+        x = fmaf(cs, dist, x);
+        y = fmaf(sn, dist, y);
+        v = fmaf(total, k.dt, v);
+        th = fmaf(oc, k.dt, th);
+        Mth<PRECISE>::sincos_(th, sn, cs);
+        feature_grad<NOT_, LT, PRECISE>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
                                         gx[t], gy[t], gv[t], gth[t]);
-        }
+    }
     float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    const float lra = k.lr * k.hdt2, lrv = k.lr * k.dt;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int tt = 0; tt < H; ++tt) {
         const int t = H - 1 - tt;
-        {
-            const float mx = gx[t] + lx, my = gy[t] + ly, mv = gv[t] + lv, mth = gth[t] + lth;
-            const float ld = fmaf(sc[t], mx, ss[t] * my);
-            const float a = u.ua[t], om = u.uw[t];
-            float ga = fmaf(k.hdt2, ld, k.dt * mv);
-            float gw = k.dt * mth;
-            ga = (a >= -8.0f && a <= 4.0f) ? ga : 0.0f;
-            gw = (om >= -4.0f && om <= 4.0f) ? gw : 0.0f;
-            lv = fmaf(fmaf(c1, sv[t], 1.0f), mv, fmaf(c2, sv[t], k.dt) * ld);
-            lth = fmaf(sd[t], fmaf(sc[t], my, -(ss[t] * mx)), mth);
-            lx = mx;
-            ly = my;
+        const float mx = gx[t] + lx, my = gy[t] + ly, mv = gv[t] + lv, mth = gth[t] + lth;
+        const float ld = fmaf(sc[t], mx, ss[t] * my);
+        const float a = u.ua[t], om = u.uw[t];
+        const bool in_a = (a >= -8.0f) && (a <= 4.0f);      // d clip / d a, inclusive (TF masks)
+        const bool in_w = fabsf(om) <= 4.0f;
+        lv = fmaf(fmaf(c1, sv[t], 1.0f), mv, fmaf(c2, sv[t], k.dt) * ld);
+        lth = fmaf(sd[t], fmaf(sc[t], my, -(ss[t] * mx)), mth);
+        lx = mx;
+        ly = my;
+        if (UPDATE && !PRECISE) {               // u <- u + lr * dR/du, constants folded
+            u.ua[t] = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
+            u.uw[t] = in_w ? fmaf(lrv, mth, om) : om;
+        } else {
+            const float ga = in_a ? fmaf(k.hdt2, ld, k.dt * mv) : 0.0f;
+            const float gw = in_w ? k.dt * mth : 0.0f;
             if (UPDATE) {                       // u <- u - lr * d(-R)/du          naive_planner.py:153
                 u.ua[t] = fmaf(k.lr, ga, a);
                 u.uw[t] = fmaf(k.lr, gw, om);
@@ -396,7 +483,8 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
 }
 
 // R(u) = sum_t w . phi(s_{t+1}), value only, reference op order (naive_planner.py:43-77).
-template <int HT, bool PRECISE>
+// The slab is a FAST (scaled) one exactly when PRECISE is false.
+template <int HT, int LT, bool PRECISE>
 __device__ __forceinline__ float rollout_reward(const KParams &k, const float *wraw, int ws, float x0, float y0,
                                                 float v0, float th0, const float *oth, int P,
                                                 const Traj<HT> &u) {
@@ -405,12 +493,12 @@ __device__ __forceinline__ float rollout_reward(const KParams &k, const float *w
     float r = 0.0f;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
-            dynamics_step<PRECISE>(x, y, v, th, u.ua[t], u.uw[t], k.dt, k.dt2, k.mu);
-            float sn, cs;
-            Mth<PRECISE>::sincos_(th, sn, cs);
-            r = __fadd_rn(r, reward_value<PRECISE>(k, wraw, ws, x, y, v, sn, oth + (size_t)t * k.NO * 2 * P,
-                                                   2 * P, P));
-        }
+        dynamics_step<PRECISE>(x, y, v, th, u.ua[t], u.uw[t], k.dt, k.dt2, k.mu);
+        float sn, cs;
+        Mth<PRECISE>::sincos_(th, sn, cs);
+        r = __fadd_rn(r, reward_value<LT, PRECISE, !PRECISE>(k, wraw, ws, x, y, v, sn,
+                                                             oth + (size_t)t * k.NO * 2 * P, 2 * P, P));
+    }
     return r;
 }
 
@@ -423,13 +511,13 @@ __device__ __forceinline__ void init_start(const KParams &k, int s, float cur_sp
     const float w0 = (m == 0) ? 0.0f : ((m == 1) ? -k.turn : k.turn);
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
-            u.ua[t] = a0;
-            u.uw[t] = w0;
-        }
+        u.ua[t] = a0;
+        u.uw[t] = w0;
+    }
 }
 
 // The complete solve for one (problem, start): n_iter SGD iterations, then the final loss.
-template <int HT, int NOT_, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE>
 __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, const float *wraw, int ws,
                                              float x0, float y0, float v0, float th0, const float *oth, int P,
                                              Traj<HT> &u) {
@@ -437,8 +525,8 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
     Mth<PRECISE>::sincos_(th0, sn0, cs0);
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
-        sgd_iteration<HT, NOT_, PRECISE, true>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
-    return -rollout_reward<HT, PRECISE>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+        sgd_iteration<HT, NOT_, LT, PRECISE, true>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
+    return -rollout_reward<HT, LT, PRECISE>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 
 }  // namespace ocd

@@ -1,14 +1,14 @@
-// ocd_inst.cu -- one (H, other cars, math mode) specialisation of k_solve / k_episode.
+// ocd_inst.cu -- one (H, other cars, lanes, math mode) specialisation of k_solve / k_episode.
 // Compiled once per combination by the Makefile:
-//   nvcc -DOCD_HT=5 -DOCD_NO=1 -DOCD_PRECISE=0 -c ocd_inst.cu -o build/inst_5_1_0.o
+//   nvcc -DOCD_HT=5 -DOCD_NO=1 -DOCD_LT=3 -DOCD_PRECISE=0 -c ocd_inst.cu -o build/inst_5_1_3_0.o
 #include "ocd_kernels.cuh"
 
-#if !defined(OCD_HT) || !defined(OCD_NO) || !defined(OCD_PRECISE)
-#error "define OCD_HT, OCD_NO and OCD_PRECISE"
+#if !defined(OCD_HT) || !defined(OCD_NO) || !defined(OCD_LT) || !defined(OCD_PRECISE)
+#error "define OCD_HT, OCD_NO, OCD_LT and OCD_PRECISE"
 #endif
 
 namespace ocd {
-template int launch_solve_t<OCD_HT, OCD_NO, (OCD_PRECISE != 0)>(const KParams &, const SolveArgs &, cudaStream_t);
-template int launch_episode_t<OCD_HT, OCD_NO, (OCD_PRECISE != 0)>(const KParams &, const ocd_scenario &,
+template int launch_solve_t<OCD_HT, OCD_NO, OCD_LT, (OCD_PRECISE != 0)>(const KParams &, const SolveArgs &, cudaStream_t);
+template int launch_episode_t<OCD_HT, OCD_NO, OCD_LT, (OCD_PRECISE != 0)>(const KParams &, const ocd_scenario &,
                                                                   const EpisodeArgs &, cudaStream_t);
 }  // namespace ocd

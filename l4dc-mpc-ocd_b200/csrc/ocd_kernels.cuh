@@ -104,15 +104,15 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
             om = oc[(size_t)(t * 2 + 1) * ocs];
         }
         other_model_step<PRECISE>(x, y, v, th, oc != nullptr, a, om, k.dt, k.dt2);
-        oth_col[(size_t)((t * k.NO + j) * 2 + 0) * P] = x;
-        oth_col[(size_t)((t * k.NO + j) * 2 + 1) * P] = y;
+        oth_col[(size_t)((t * k.NO + j) * 2 + 0) * P] = slab_x<PRECISE>(x);
+        oth_col[(size_t)((t * k.NO + j) * 2 + 1) * P] = slab_y<PRECISE>(y);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_solve
 // ---------------------------------------------------------------------------------------------
-template <int HT, int NOT_, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE>
 __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ float smem_raw[];
     const int P = a.P;
@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ K
     __syncthreads();
 
     const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
-    const GradW gw = make_gradw(k, m.wraw + p, P);
+    const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     Traj<HT> u;
     init_start<HT>(k, s, a.cur_speed ? a.cur_speed[b] : v0, u);
-    const float loss = solve_start<HT, NOT_, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+    const float loss = solve_start<HT, NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
     m.loss[s * P + p] = loss;
     if (live) {
         a.losses[(size_t)s * B + b] = loss;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ K
 // ---------------------------------------------------------------------------------------------
 // k_episode
 // ---------------------------------------------------------------------------------------------
-template <int HT, int NOT_, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE>
 __global__ void __launch_bounds__(kMaxThreads)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ float smem_raw[];
@@ -206,7 +206,7 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
         if (a.unlucky_idx) unlucky = a.unlucky_idx[b];
     }
     __syncthreads();
-    const GradW gw = make_gradw(k, m.wraw + p, P);
+    const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     float ret = 0.0f;
 
     for (int i = 0; i < a.T; ++i) {
@@ -223,7 +223,7 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
                 const float x = m.world[p], y = m.world[P + p], v = m.world[2 * P + p], th = m.world[3 * P + p];
                 float sn, cs;
                 Mth<PRECISE>::sincos_(th, sn, cs);
-                ret = __fadd_rn(ret, reward_value<PRECISE>(k, m.wtrue, 1, x, y, v, sn, m.world + 4 * P + p,
+                ret = __fadd_rn(ret, reward_value<LT, PRECISE, false>(k, m.wtrue, 1, x, y, v, sn, m.world + 4 * P + p,
                                                            4 * P, P));
             }
             // what the planner assumes about the other cars (planner_car.py:58-80, naive_planner.py:47-67)
@@ -238,8 +238,8 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
                         oo = in_plan ? sc.plan[j][t][1] : sc.control[j][1];
                     }
                     other_model_step<PRECISE>(x, y, v, th, k.other_mode == 1, oa, oo, k.dt, k.dt2);
-                    m.oth[(size_t)((t * k.NO + j) * 2 + 0) * P + p] = x;
-                    m.oth[(size_t)((t * k.NO + j) * 2 + 1) * P + p] = y;
+                    m.oth[(size_t)((t * k.NO + j) * 2 + 0) * P + p] = slab_x<PRECISE>(x);
+                    m.oth[(size_t)((t * k.NO + j) * 2 + 1) * P + p] = slab_y<PRECISE>(y);
                 }
             }
         }
@@ -248,7 +248,7 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
         const float x0 = m.world[p], y0 = m.world[P + p], v0 = m.world[2 * P + p], th0 = m.world[3 * P + p];
         Traj<HT> u;
         init_start<HT>(k, s, v0, u);
-        const float loss = solve_start<HT, NOT_, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+        const float loss = solve_start<HT, NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
         m.loss[s * P + p] = loss;
         m.u0[(s * 2 + 0) * P + p] = u.ua[0];
         m.u0[(s * 2 + 1) * P + p] = u.uw[0];
@@ -306,10 +306,10 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
-template <int HT, int NOT_, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false) * sizeof(float);
-    auto kern = k_solve<HT, NOT_, PRECISE>;
+    auto kern = k_solve<HT, NOT_, LT, PRECISE>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
@@ -317,10 +317,10 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     return cuda_status();
 }
 
-template <int HT, int NOT_, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true) * sizeof(float);
-    auto kern = k_episode<HT, NOT_, PRECISE>;
+    auto kern = k_episode<HT, NOT_, LT, PRECISE>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
