@@ -350,10 +350,22 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
     {
         const float ax = fabsf(x);
         const float q = ax - k.thr_lo;
-        if (PRECISE ? (q > 0.0f) : __any_sync(OCD_FULL, q > 0.0f)) {
-            float f = 0.0f, df = 0.0f;
-            if (q > 0.0f) fence_inside<PRECISE>(k, x, ax, q, f, df);
-            gx = fmaf(w.wfence, df, gx);
+        if (PRECISE) {
+            if (q > 0.0f) {
+                float f, df;
+                fence_inside<true>(k, x, ax, q, f, df);
+                gx = fmaf(w.wfence, df, gx);
+            }
+        } else if (__any_sync(OCD_FULL, q > 0.0f)) {
+            // T = F1/(F1+F2) = 1/(1 + exp(r1 - r2)), r1 = 1/(shape q), r2 = 1/(shape (width - q));
+            // dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping q and width-q to a tiny positive number
+            // makes the exponential saturate: T = 0, dT = 0 below the ramp and T = 1, dT = 0 above it,
+            // so the three regions need no branch.
+            const float r1 = Mth<false>::rcp_(k.fshape * fmaxf(q, 1e-9f));
+            const float r2 = Mth<false>::rcp_(k.fshape * fmaxf(k.thr_w - q, 1e-9f));
+            const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_((r1 - r2) * OCD_LOG2E));
+            const float dT = (T * (1.0f - T)) * (k.fshape * fmaf(r1, r1, r2 * r2));
+            gx = fmaf(w.wfence, copysignf(fmaf(dT, ax, T), x), gx);
         }
     }
 }
