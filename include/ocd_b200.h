@@ -99,6 +99,15 @@ int ocd_dynamics_step_batch(const float *state /*[4][B]*/, const float *control 
                             float dt, float friction, const float *friction_b /*[B] or NULL*/,
                             float *next_state /*[4][B]*/, int64_t B, void *stream);
 
+/* The smooth helpers of interact_drive/math_utils.py, evaluated with the kernels' precise math for
+ * B points (kind selects the function; p0, p1 are its parameters):
+ *   OCD_SMOOTH_F          _f(x, shape=p0)                        math_utils.py:7-31
+ *   OCD_SMOOTH_THRESHOLD  smooth_threshold(threshold=p0, width=p1, c=5)(z)   math_utils.py:59-97
+ *   OCD_SMOOTH_BUMP       smooth_bump(start=p0, end=p1)(z)        math_utils.py:135-180 */
+enum { OCD_SMOOTH_F = 0, OCD_SMOOTH_THRESHOLD = 1, OCD_SMOOTH_BUMP = 2 };
+int ocd_smooth_batch(int kind, const float *z /*[B]*/, double p0, double p1, float *out /*[B]*/,
+                     int64_t B, void *stream);
+
 /* ThreeLaneTestCar.features (experiments/merging.py:32-83) for B world states. */
 int ocd_features_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
                        float *phi /*[K][B]*/, int64_t B, void *stream);

@@ -10,3 +10,28 @@ from .engine import (  # noqa: F401
 )
 
 __all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "device_count"]
+
+
+def install_as_reference() -> None:
+    """Make `import interact_drive...` / `import experiments...` resolve to this package's drop-in
+    mirror, so that scripts written against the reference run on the engine unchanged:
+
+        import l4dc_mpc_ocd_b200; l4dc_mpc_ocd_b200.install_as_reference()
+        from interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env
+    """
+    import importlib
+    import sys
+    pkg = __name__
+    for name in ("interact_drive", "interact_drive.simulation_utils", "interact_drive.math_utils",
+                 "interact_drive.world", "interact_drive.car", "interact_drive.car.car",
+                 "interact_drive.car.fixed_control_car", "interact_drive.car.fixed_velocity_car",
+                 "interact_drive.car.fixed_plan_car", "interact_drive.car.planner_car",
+                 "interact_drive.car.linear_reward_car", "interact_drive.planner",
+                 "interact_drive.planner.car_planner", "interact_drive.planner.naive_planner",
+                 "interact_drive.reward_design", "interact_drive.reward_design.mpc_ord", "experiments",
+                 "experiments.merging", "experiments.local_opt_scenario", "experiments.replanning_world",
+                 "experiments.run_mpc_ord"):
+        sys.modules[name] = importlib.import_module(pkg + "." + name)
+
+
+__all__.append("install_as_reference")

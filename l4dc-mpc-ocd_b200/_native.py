@@ -15,6 +15,7 @@ LIB_PATH = _HERE / "libocd_b200.so"
 ABI_VERSION = 1
 MAX_LANES, MAX_OTHER, MAX_PLAN, MAX_H, MAX_STARTS = 4, 7, 16, 64, 6
 OK, EINVAL, EUNSUP, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+SMOOTH_F, SMOOTH_THRESHOLD, SMOOTH_BUMP = 0, 1, 2
 
 
 class OcdError(RuntimeError):
@@ -57,6 +58,7 @@ _PROTOTYPES = {
     "ocd_num_starts": (C.c_int, [_P]),
     "ocd_device_count": (C.c_int, []),
     "ocd_dynamics_step_batch": (C.c_int, [_P, _P, C.c_float, C.c_float, _P, _P, _I64, _P]),
+    "ocd_smooth_batch": (C.c_int, [C.c_int, _P, C.c_double, C.c_double, _P, _I64, _P]),
     "ocd_features_batch": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ocd_reward_grad_batch": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P]),
     "ocd_solve_batch": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),

@@ -103,6 +103,28 @@ k_dynamics(const float *state, const float *control, float dt, float dt2, float 
     next[b] = x; next[B + b] = y; next[2 * B + b] = v; next[3 * B + b] = th;
 }
 
+// math_utils.py helpers as operators (precise math, reference op order)
+__global__ void __launch_bounds__(256)
+k_smooth(int kind, const float *z, float a, float b, float c, float *out, long long B) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float x = z[i];
+    float r = 0.0f;
+    if (kind == OCD_SMOOTH_F) {                    // a = shape
+        if (x > 0.0f) r = expf(__fdiv_rn(-1.0f, __fmul_rn(a, x)));
+    } else if (kind == OCD_SMOOTH_THRESHOLD) {     // a = threshold - width, b = width, c = shape
+        const float q = __fsub_rn(x, a), u2 = __fsub_rn(b, q);
+        const float F1 = q > 0.0f ? expf(__fdiv_rn(-1.0f, __fmul_rn(c, q))) : 0.0f;
+        const float F2 = u2 > 0.0f ? expf(__fdiv_rn(-1.0f, __fmul_rn(c, u2))) : 0.0f;
+        r = __fdiv_rn(F1, __fadd_rn(F1, F2));
+    } else {                                       // a = start, b = end
+        const float width = __fmul_rn(__fsub_rn(b, a), 0.5f), center = __fmul_rn(__fadd_rn(a, b), 0.5f);
+        const float n = __fdiv_rn(__fsub_rn(x, center), width);
+        if (__fmul_rn(n, n) < 1.0f) r = expf(__fadd_rn(__fdiv_rn(-1.0f, __fsub_rn(1.0f, __fmul_rn(n, n))), 1.0f));
+    }
+    out[i] = r;
+}
+
 // dependent-free FMA loop: 8 independent chains per thread, 2 FLOP per FMA
 __global__ void __launch_bounds__(256) k_fp32_peak(int iters, float *sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
@@ -226,6 +248,27 @@ int ocd_dynamics_step_batch(const float *state, const float *control, float dt, 
     const float dt2 = (float)((double)dt * (double)dt);
     k_dynamics<true><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         state, control, dt, dt2, friction, friction_b, next_state, B);
+    return cuda_status();
+}
+
+int ocd_smooth_batch(int kind, const float *z, double p0, double p1, float *out, int64_t B, void *stream) {
+    if (B == 0) return OCD_OK;
+    if (!z || !out || B < 0) return OCD_EINVAL;
+    float a, b = 0.0f, c = 0.0f;
+    if (kind == OCD_SMOOTH_F) {
+        a = (float)p0;
+    } else if (kind == OCD_SMOOTH_THRESHOLD) {
+        if (!(p1 > 0.0)) return OCD_EINVAL;
+        a = (float)(p0 - p1);          // Python-double difference, cast once (math_utils.py:92)
+        b = (float)p1;
+        c = (float)(5.0 / p1);
+    } else if (kind == OCD_SMOOTH_BUMP) {
+        a = (float)p0;
+        b = (float)p1;
+    } else {
+        return OCD_EINVAL;
+    }
+    k_smooth<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, z, a, b, c, out, B);
     return cuda_status();
 }
 

@@ -278,6 +278,18 @@ class Engine:
         self._kernel_launches += 1 if B else 0
         return phi.t().contiguous()
 
+    def smooth(self, kind: int, z, p0: float, p1: float = 0.0) -> torch.Tensor:
+        """_f / smooth_threshold / smooth_bump of interact_drive/math_utils.py at the points z."""
+        zt = torch.as_tensor(z, dtype=torch.float32, device=self.device)
+        shape = zt.shape
+        zt = zt.reshape(-1).contiguous()
+        out = torch.empty_like(zt)
+        with torch.cuda.device(self.device):
+            rc = N.lib.ocd_smooth_batch(int(kind), _ptr(zt), float(p0), float(p1), _ptr(out), zt.numel(), self._stream())
+        N.check(rc, "ocd_smooth_batch")
+        self._kernel_launches += 1 if zt.numel() else 0
+        return out.reshape(shape)
+
     def dynamics(self, state, control, dt: float, friction) -> torch.Tensor:
         """state [B, 4], control [B, 2], friction scalar or [B] -> next state [B, 4]."""
         s = torch.as_tensor(state, dtype=torch.float32, device=self.device)

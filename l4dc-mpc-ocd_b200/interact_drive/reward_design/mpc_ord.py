@@ -1,0 +1,231 @@
+"""MPC_ORD and the finite_horizon scenario: mirror of interact_drive/reward_design/mpc_ord.py of the
+reference (MPC_ORD :15-158, finite_horizon_env :162-207).
+
+The reference evaluates a weight vector by resetting a Python world and stepping it `designer_horizon`
+times for every initial state and sample, one full MPC solve per step.  Here a whole evaluation -- all
+initial states x samples, and in `eval_weights_batch` all candidates of a CMA-ES generation too -- is
+one launch of the episode kernel (`ocd_episode_batch`); the Python world is only compiled into the
+POD description the kernel needs."""
+from __future__ import annotations
+
+import pickle
+import sys
+import time
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.stats
+
+from ... import cmaes as _cma
+from ... import parallel as _par
+from ...batched import compile_world, unlucky_sequence
+from ...experiments.merging import ThreeLaneCarWorld, ThreeLaneTestCar
+from ...runtime import as_f32, get_engine
+from ..car import FixedVelocityCar
+
+
+class list2(list):
+    """A list that can carry attributes (`history.seed`), pickled under the reference's module path so
+    that the reference's loaders (experiments/generalization_data.py:18) read our histories."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+
+
+list2.__module__ = "interact_drive.reward_design.mpc_ord"
+
+
+def _truncnorm_sample(mean, std, rang):
+    a, b = (rang[0] - mean) / std, (rang[1] - mean) / std
+    return np.squeeze(scipy.stats.truncnorm.rvs(a, b) * std + mean)
+
+
+def sample_init_state(env_seed, x, y, speed):
+    """Robot initial state: three truncated normals drawn under np.random.seed(env_seed), heading pi/2
+    (reference mpc_ord.py:171-181; scipy-version dependent, so parity tests pass states explicitly)."""
+    np.random.seed(seed=env_seed)
+    return np.array([_truncnorm_sample(*x), _truncnorm_sample(*y), _truncnorm_sample(*speed), np.pi / 2])
+
+
+class MPC_ORD:
+    """Evaluates / optimises surrogate reward weights for a planning car by the TRUE-weight return of
+    the receding-horizon episodes it produces."""
+
+    def __init__(self, world, car, init_car_states, designer_horizon, save_path=None, num_samples=1, *,
+                 verbose: bool = True, device: Optional[int] = None):
+        self.world, self.car = world, car
+        self.designer_horizon = designer_horizon
+        self.init_car_states = init_car_states
+        self.save_path = save_path
+        w = np.asarray(car.weights)
+        self.designer_weights = w / np.linalg.norm(w)
+        self.weight_dim = len(w)
+        self.history = list2()
+        self.iter = 0
+        self.should_save_history = False
+        self.done = False
+        self.num_samples = num_samples
+        self.verbose = verbose
+        self._device = device
+        self.program = compile_world(world, car)
+        self.kernel_launches = 0
+
+    # -- the batched core ------------------------------------------------------------------------------
+    @staticmethod
+    def _planning_weights(weights) -> np.ndarray:
+        """What the planner ends up with: normalised in eval_weights, again in eval_weights_for_init and
+        again in the car's setter, in float64, then cast (reference :120, :71, linear_reward_car.py:47)."""
+        w = np.asarray(weights, dtype=np.float64)
+        if w.ndim == 2:
+            w = w[0]
+        for _ in range(3):
+            w = w / np.linalg.norm(w)
+        return w.astype(np.float32)
+
+    def episode_returns(self, weight_matrix, inits: Optional[Sequence] = None, trace: bool = False):
+        """weight_matrix [n_cand, K] (raw candidates) x inits [n_init, 4] x num_samples ->
+        returns [n_cand, n_init, num_samples] of sum_t true_w . features(past_state_t), one launch.
+        With trace=True also the per-step controls/states of every episode (host arrays)."""
+        W = np.stack([self._planning_weights(w) for w in np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))])
+        inits = self.init_car_states if inits is None else inits
+        I = np.stack([as_f32(s, (4,)) for s in inits])
+        nc, ni, ns = W.shape[0], I.shape[0], self.num_samples
+        robot = np.repeat(np.tile(I, (nc, 1)), ns, axis=0)                       # [nc*ni*ns, 4]
+        widx = np.repeat(np.arange(nc, dtype=np.int32), ni * ns)
+        unlucky = None
+        if self.program.replanning:
+            # every evaluation of one init resets the world num_samples times (reference :87-89); all
+            # candidates see the same toggle sequence as a serial run would give the first of them
+            seq = unlucky_sequence(self.world, ni * ns)
+            unlucky = np.tile(np.asarray(seq, np.int32), nc)
+        eng = get_engine(self._device)
+        B = robot.shape[0]
+        rank, ws = _par.world()
+        if ws > 1 and not trace:
+            # one process per GPU: this rank runs its contiguous shard of the episodes, then the
+            # per-episode returns are all-gathered (the path's only exchange step)
+            def run(idx):
+                o = eng.episodes(self.program.params, self.program.scenario, robot[idx], W,
+                                 as_f32(self.designer_weights), self.designer_horizon, weight_idx=widx[idx],
+                                 unlucky_idx=None if unlucky is None else unlucky[idx], final_world=True)
+                run.final = o["final_world"]
+                return o["returns"]
+            returns = _par.sharded_returns(run, B)
+            out = dict(returns=returns, final_world=run.final)
+        else:
+            out = eng.episodes(self.program.params, self.program.scenario, robot, W, as_f32(self.designer_weights),
+                               self.designer_horizon, weight_idx=widx, unlucky_idx=unlucky, trace=trace,
+                               final_world=True)
+        self.kernel_launches += 1
+        ret = out["returns"].cpu().numpy().reshape(nc, ni, ns)
+        # leave the Python objects the way a serial evaluation would: last weights, last init, final state
+        self.car.weights = W[-1]
+        self.car.init_state = I[-1]
+        final = out["final_world"].cpu().numpy()[-1]
+        for c, s in zip(self.world.cars, final):
+            c.state = s
+        if trace:
+            return ret, {k: out[k].cpu().numpy() for k in ("controls", "best", "states")}
+        return ret
+
+    # -- reference API -----------------------------------------------------------------------------------
+    def eval_weights_for_init(self, init, weights, render=False, heatmap_show=False):
+        """Return of `weights` from one initial state, summed over the samples (reference :67-106)."""
+        if render:
+            raise NotImplementedError("rendering is outside the batched MPC engine's scope")
+        r = self.episode_returns([weights], [init], trace=self.car.debug)
+        if self.car.debug:
+            r, tr = r
+            ctl, st = tr["controls"][-1], tr["states"][-1]          # the last sample, like a serial run leaves
+            for j, c in enumerate(self.world.cars):
+                c.past_traj = [(st[t, j].copy(), ctl[t].copy() if j == 0 else None) for t in range(st.shape[0])]
+        total = np.float32(r[0, 0].sum(dtype=np.float32))
+        if self.verbose:
+            print('init', init, 'weights', self.car.weights, '\tgave return:', total, 'time', time.time())
+        return total
+
+    def eval_weights(self, weights, gif=None, heatmap_show=False):
+        """-> MINUS the return of `weights` summed over the initial states and averaged over samples
+        (reference :109-151): the callable CMA-ES minimises."""
+        if gif:
+            raise NotImplementedError("gif rendering is outside the batched MPC engine's scope")
+        return float(self.eval_weights_batch([weights])[0])
+
+    def eval_weights_batch(self, weight_matrix) -> np.ndarray:
+        """eval_weights for every row of weight_matrix in ONE launch; history and iteration counter
+        advance exactly as if the rows had been evaluated one after the other."""
+        W = [np.asarray(w, dtype=np.float64) for w in weight_matrix]
+        W = [w[0] if w.ndim == 2 else w for w in W]
+        ret = self.episode_returns(W)                                 # [nc, ni, ns]
+        totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
+        for w, total in zip(W, totals):
+            wn = w / np.linalg.norm(w)
+            if self.verbose:
+                print('ITERATION', self.iter)
+                print('eval', wn)
+                print('eval reward for weights:', total, '\n\n')
+            self.history.append((wn, total))
+            self.iter += 1
+        if self.should_save_history and self.save_path is not None:
+            self.save_history()
+        return -totals
+
+    def optimize_cmaes(self, seed=1, sigma0=0.1, **stop):
+        """CMA-ES over the weights starting from the designer's (reference :33-45); every generation is
+        one launch.  `stop` forwards maxfevals / maxiter / tolfun / tolx."""
+        self.history.seed = seed
+        assert seed != 0
+        assert not self.done
+        self.should_save_history = True
+        self.eval_weights(self.designer_weights)
+        x, es = _cma.fmin2(self.eval_weights, list(self.designer_weights), sigma0, dict(seed=seed, **stop),
+                           batch_objective=self.eval_weights_batch)
+        self.should_save_history = False
+        self.done = True
+        return x
+
+    def optimize_random_search(self, n_iter=1000, seed=1, chunk=256):
+        """Uniform random search in [-1, 1]^K (reference :47-65), `chunk` candidates per launch."""
+        self.history.seed = seed
+        assert not self.done
+        self.should_save_history = True
+        if self.verbose:
+            print("\n\nSTARTING RANDOM SEARCH")
+        self.iter = 0
+        self.eval_weights(self.designer_weights)
+        np.random.seed(seed)
+        cands = [np.random.rand(*self.designer_weights.shape) * 2 - 1 for _ in range(n_iter)]
+        for i in range(0, n_iter, chunk):
+            self.eval_weights_batch(cands[i:i + chunk])
+        self.should_save_history = False
+        self.done = True
+        return max(self.history, key=lambda a: a[1])
+
+    def save_history(self):
+        assert self.save_path is not None
+        # list2 pickles as interact_drive.reward_design.mpc_ord.list2 (the reference's path)
+        pkg = __name__.rsplit(".interact_drive.", 1)[0]
+        for alias in ("interact_drive", "interact_drive.reward_design", "interact_drive.reward_design.mpc_ord"):
+            sys.modules.setdefault(alias, sys.modules[pkg + "." + alias])
+        if getattr(sys.modules["interact_drive.reward_design.mpc_ord"], "list2", None) is not list2:
+            raise RuntimeError("another interact_drive.reward_design.mpc_ord is imported; cannot pickle history")
+        with open(self.save_path, 'wb') as file:
+            pickle.dump(self.history, file)
+        if self.verbose:
+            print('Wrote results so far to', self.save_path)
+
+
+def finite_horizon_env(horizon=5, env_seeds=[1], debug=True, extra_inits=False):
+    """The finite-horizon scenario (reference mpc_ord.py:162-207): a three-lane road, the planning car
+    behind a slower FixedVelocityCar in its lane.  -> (car, world, init_states)."""
+    init_states = [sample_init_state(s, (0, 0.04, (-0.1, 0.1)), (-0.9, 0.02, (-0.95, -0.85)), (0.8, 0.03, (0.7, 0.9)))
+                   for s in env_seeds]
+    world = ThreeLaneCarWorld(visualizer_args=dict(name="Switch Lanes"))
+    planner_args = dict(n_iter=200 if horizon == 6 else 100, extra_inits=extra_inits)
+    our_car = ThreeLaneTestCar(world, init_state=init_states[0], horizon=horizon,
+                               weights=np.array([-5, 0., 0., 0., -6., -50, -50]), debug=debug,
+                               planner_args=planner_args)
+    other_car = FixedVelocityCar(world, np.array([0, -0.6, 0.5, np.pi / 2]), color="gray", opacity=0.8, debug=debug)
+    world.add_cars([our_car, other_car])
+    world.reset()
+    return our_car, world, init_states

@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: one process per GPU, problems sharded on the batch axis.
+
+Every (candidate x initial state x sample) episode -- and every start inside it -- is independent
+for its whole length, so the only exchange step of the path is one all-gather of the per-episode
+float32 returns per CMA-ES generation (4 bytes per episode; latency-bound).  Ranks then hold the
+same returns and run the identical optimiser update, so nothing else is communicated."""
+from __future__ import annotations
+
+from typing import Callable, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the default process group; (0, 1) outside torch.distributed."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(B: int, rank: int, world_size: int) -> Tuple[int, int, int]:
+    """Contiguous shard [lo, hi) of B problems for `rank`, and the padded per-rank length `per`
+    (every rank launches `per` problems so that the all-gather is regular)."""
+    per = (B + world_size - 1) // world_size if B else 0
+    lo = min(B, rank * per)
+    hi = min(B, lo + per)
+    return lo, hi, per
+
+
+def shard_indices(B: int, rank: int, world_size: int) -> np.ndarray:
+    """Problem indices this rank evaluates: its shard, padded by repeating the last problem of the
+    batch (padding results are dropped after the gather)."""
+    lo, hi, per = shard_bounds(B, rank, world_size)
+    idx = np.arange(lo, lo + per)
+    return np.minimum(idx, B - 1) if B else idx
+
+
+def gather_returns(local: torch.Tensor, B: int) -> torch.Tensor:
+    """local [per] on every rank -> the first B entries of the rank-ordered concatenation."""
+    rank, ws = world()
+    if ws == 1:
+        return local[:B]
+    out = torch.empty((local.numel() * ws,), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local.contiguous())
+    else:                                   # gloo (CPU tests)
+        parts = [torch.empty_like(local) for _ in range(ws)]
+        dist.all_gather(parts, local.contiguous())
+        out = torch.cat(parts)
+    return out[:B]
+
+
+def sharded_returns(evaluate: Callable[[np.ndarray], torch.Tensor], B: int) -> torch.Tensor:
+    """Run `evaluate(indices) -> returns [len(indices)]` on this rank's shard of range(B) and
+    all-gather: every rank gets all B returns."""
+    rank, ws = world()
+    idx = shard_indices(B, rank, ws)
+    return gather_returns(evaluate(idx), B)

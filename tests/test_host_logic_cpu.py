@@ -1,0 +1,193 @@
+"""Host-side logic that needs no GPU: scenario constructors, the world compiler, weight
+normalisation, CMA-ES, sharding arithmetic, the synthetic generator and bench.py's reference arm."""
+import json
+import pickle
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import l4dc_mpc_ocd_b200 as ocd
+from l4dc_mpc_ocd_b200 import cmaes, parallel, synthetic
+from l4dc_mpc_ocd_b200.batched import compile_world, unlucky_sequence
+from l4dc_mpc_ocd_b200.experiments.local_opt_scenario import local_opt_env
+from l4dc_mpc_ocd_b200.experiments.replanning_world import setup_world, og_weights
+from l4dc_mpc_ocd_b200.experiments import run_mpc_ord
+from l4dc_mpc_ocd_b200.interact_drive.car import FixedPlanCar, FixedVelocityCar, PlannerCar
+from l4dc_mpc_ocd_b200.interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env, list2
+from l4dc_mpc_ocd_b200.interact_drive.world import StraightLane, ThreeLaneCarWorld, TwoLaneCarWorld
+from conftest import load_golden
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_lane_geometry():
+    assert ThreeLaneCarWorld().lane_medians() == pytest.approx((-0.1, 0.0, 0.1))
+    assert TwoLaneCarWorld().lane_medians() == pytest.approx((-0.05, 0.05))
+    lane = StraightLane((0.0, -5.), (0.0, 10.), 0.1)
+    assert lane.dist2median((0.03, 7.0)) == pytest.approx(0.03 ** 2)
+    assert lane.shifted(-1).dist2median((0.1, 0.0)) == pytest.approx(0.0)
+    with pytest.raises(ValueError):
+        StraightLane((0, 0), (1, 1), 0.1).median_x
+
+
+def test_scenario_constructors_and_compiler():
+    car, world, inits = finite_horizon_env(env_seeds=[1000000, 1000001])
+    assert len(inits) == 2 and inits[0][3] == pytest.approx(np.pi / 2)
+    assert -0.1 <= inits[0][0] <= 0.1 and -0.95 <= inits[0][1] <= -0.85 and 0.7 <= inits[0][2] <= 0.9
+    np.testing.assert_allclose(car.weights, np.array([-5, 0, 0, 0, -6, -50, -50]) / np.linalg.norm([-5, 0, 0, 0, -6, -50, -50]),
+                               atol=1e-7)
+    prog = compile_world(world, car)
+    assert (prog.params.H, prog.params.C, prog.params.n_iter, prog.params.other_mode) == (5, 2, 100, 0)
+    assert prog.scenario.kind == [0] and prog.scenario.friction == [0.0] and not prog.replanning
+    car6, world6, _ = finite_horizon_env(horizon=6, extra_inits=True)
+    p6 = compile_world(world6, car6).params
+    assert (p6.H, p6.n_iter, p6.extra_inits, p6.S) == (6, 200, True, 6)
+
+    car, world, inits = local_opt_env(env_seeds=[5])
+    assert -0.12 <= inits[0][0] <= -0.08 and 0.9 <= inits[0][2] <= 1.1
+    assert compile_world(world, car).scenario.init_state[0][1] == pytest.approx(-0.9)
+
+    car, world, inits = setup_world(env_seeds=[5])
+    prog = compile_world(world, car)
+    assert prog.replanning and prog.scenario.critical_t == 4 and prog.scenario.kind == [1, 1]
+    assert prog.scenario.friction == [0.2, 0.2]               # FixedPlanCar keeps the Car default
+    assert (prog.params.C, prog.params.L, prog.params.num_lanes, prog.params.other_mode) == (3, 2, 2, 1)
+    assert prog.params.target_speed == pytest.approx(1.2)
+    np.testing.assert_allclose(prog.scenario.plan[0][1], [0.7, 2.7])
+    np.testing.assert_allclose(prog.scenario.plan[1][3], [0.0, 2.7])
+    np.testing.assert_allclose(car.weights, og_weights, atol=1e-7)
+    # ctor reset already toggled once (reference replanning_world.py:93): the next resets give 1, 2, 1
+    assert world.unlucky_car_idx == 2
+    assert unlucky_sequence(world, 3) == [1, 2, 1] and world.unlucky_car_idx == 1
+
+
+def test_known_other_plans_replay_from_index_zero():
+    car, world, _ = setup_world(env_seeds=[5])
+    world.cars[1].t = 3            # the other car's own clock must not matter (quirk Q4)
+    plans = car.known_other_plans()
+    assert len(plans) == 3 and plans[0].shape == (5, 2) and not plans[0].any()
+    np.testing.assert_allclose(plans[1], [[0, 0], [0.7, 2.7], [0, 0], [0, -2.7], [0, 0]])
+    np.testing.assert_allclose(plans[2], [[0, 0], [0.7, -2.7], [0, 0], [0, 2.7], [0, 0]])
+
+
+def test_compile_world_rejects_what_the_kernel_cannot_run():
+    world = ThreeLaneCarWorld()
+    a = PlannerCar(world, [0, 0, 1, 0], horizon=5)
+    world.add_car(a)
+    with pytest.raises(TypeError):
+        compile_world(world, a)
+    car, world, _ = finite_horizon_env()
+    world.add_car(PlannerCar(world, [0, 0, 1, 0], horizon=5))
+    with pytest.raises(TypeError):
+        compile_world(world, car)
+    car, world, _ = finite_horizon_env()
+    car.planner_args["leaf_evaluation"] = lambda s, u: 0
+    with pytest.raises(TypeError):
+        compile_world(world, car)
+
+
+def test_triple_normalisation_matches_reference():
+    e = load_golden("episode_local_opt_scaled_short.json")
+    w = MPC_ORD._planning_weights(np.asarray(e["weights_in"]))
+    np.testing.assert_allclose(w, np.asarray(e["plan_weights"], np.float32), atol=1e-7)
+    np.testing.assert_allclose(MPC_ORD._planning_weights(np.asarray(e["weights_in"])[None]), w)
+
+
+def test_linear_reward_car_weight_setter():
+    car, world, _ = finite_horizon_env()
+    car.weights = [0, 3, 0, 4, 0, 0, 0]
+    np.testing.assert_allclose(car.weights, [0, 0.6, 0, 0.8, 0, 0, 0], atol=1e-7)
+    assert car.weights.dtype == np.float32
+
+
+def test_fixed_plan_car_schedule_without_dynamics():
+    world = TwoLaneCarWorld()
+    c = FixedPlanCar(world, [0, 0, 1, 0], plan=[[1, 0], [2, 0]], default_control=[9, 9])
+    c.reset()
+    np.testing.assert_allclose(c.control, [1, 0])
+    assert c.control_already_determined_for_current_step and c.friction == 0.2
+    v = FixedVelocityCar(world, [0, 0, 1, 0])
+    assert v.friction == 0.0 and not v.control.any()
+
+
+def test_cmaes_minimises():
+    f = lambda x: float(np.sum((np.asarray(x) - np.arange(7) / 10.0) ** 2))
+    x, es = cmaes.fmin2(f, [0.0] * 7, 0.3, {"seed": 3, "maxfevals": 3000})
+    assert es.lam == 9 and es.mu == 4                      # pycma defaults for N = 7 (4 + floor(3 ln 7))
+    assert f(x) < 1e-8
+    calls = []
+    xb, esb = cmaes.fmin2(None, [0.0] * 7, 0.3, {"seed": 3, "maxfevals": 3000},
+                          batch_objective=lambda P: (calls.append(len(P)), [f(p) for p in P])[1])
+    np.testing.assert_array_equal(x, xb)                    # same seed, same path, one call per generation
+    assert set(calls) == {9}
+    ros = lambda x: float(sum(100 * (x[i + 1] - x[i] ** 2) ** 2 + (1 - x[i]) ** 2 for i in range(len(x) - 1)))
+    xr, _ = cmaes.fmin2(ros, [0.0] * 4, 0.5, {"seed": 1, "maxfevals": 20000})
+    assert ros(xr) < 1e-6
+
+
+def test_history_pickles_under_the_reference_path(tmp_path):
+    h = list2()
+    h.seed = 11
+    h.append((np.ones(3), -1.5))
+    class Holder:
+        save_path, history, verbose = str(tmp_path / "h.pkl"), h, False
+    MPC_ORD.save_history(Holder)
+    raw = (tmp_path / "h.pkl").read_bytes()
+    assert b"interact_drive.reward_design.mpc_ord" in raw and b"l4dc" not in raw
+    back = pickle.loads(raw)
+    assert back.seed == 11 and back[0][1] == -1.5
+
+
+def test_sharding_arithmetic():
+    for B in (0, 1, 7, 45, 90, 1000):
+        for ws in (1, 2, 4, 8):
+            seen = []
+            for r in range(ws):
+                lo, hi, per = parallel.shard_bounds(B, r, ws)
+                idx = parallel.shard_indices(B, r, ws)
+                assert len(idx) == per and (B == 0 or idx.max() <= B - 1)
+                seen += list(range(lo, hi))
+            assert seen == list(range(B))
+    assert parallel.world() == (0, 1)
+
+
+def test_synthetic_batch_and_flop_model():
+    b = synthetic.make_batch(1000, C=4)
+    assert b["world"].shape == (1000, 4, 4) and b["weights"].shape == (200, 7) and b["weight_idx"].max() == 199
+    np.testing.assert_allclose(np.linalg.norm(b["weights"], axis=1), 1.0, atol=1e-6)
+    assert np.all(np.abs(b["world"][:, 0, 0]) <= 0.1) and np.all(b["world"][:, :, 3] == np.float32(np.pi / 2))
+    # 300 030 FLOP per finite_horizon solve, 337 740 per replanning solve
+    assert synthetic.flops_per_solve(5, 2, 3) == 300030
+    assert synthetic.flops_per_solve(5, 3, 2) == 337740
+
+
+def test_cli_parsing_is_the_reference_one():
+    with pytest.raises(SystemExit):
+        run_mpc_ord.main(["nowhere", "cmaes"])
+    with pytest.raises(AssertionError):
+        run_mpc_ord.main(["finite_horizon", "cmaes", "--seed", "0"])
+    assert set(run_mpc_ord.envs) == {"local_opt", "finite_horizon", "replanning"}
+    assert run_mpc_ord.envs["replanning"]["num_eval_samples"] == 2 and run_mpc_ord.envs["replanning"]["eval_horizon"] == 20
+    assert run_mpc_ord.fmt(np.array([1.0, 2.0])) == "[1. 2.]"
+
+
+def test_install_as_reference_aliases():
+    ocd.install_as_reference()
+    import interact_drive.planner.naive_planner as npl
+    import experiments.merging as mg
+    from interact_drive.car import LinearRewardCar
+    assert npl.NaivePlanner is ocd.interact_drive.planner.naive_planner.NaivePlanner
+    assert issubclass(mg.ThreeLaneTestCar, LinearRewardCar)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, check=True, timeout=600)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mpc_solves_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    assert "workload" in line["config"]

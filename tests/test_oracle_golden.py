@@ -1,0 +1,167 @@
+"""Pins the CPU oracle (oracle/: C restatement of the reference's planner path) against the golden
+vectors produced by the reference's own unmodified Python (tests/golden/make_golden.py) and against
+the reference's known-answer tests.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import load_golden
+
+F32 = np.float32
+
+
+def _params(c, **kw):
+    st = np.asarray(c.get("state", c.get("init_state")), F32)
+    return O.OracleParams(C=st.shape[0], lane_x=tuple(c["lane_x"]), num_lanes=c["num_lanes"],
+                          target_speed=c["target_speed"], **kw)
+
+
+def test_dynamics_known_answers_and_golden():
+    g = load_golden("primitives.json")
+    for c in g["dynamics"]:
+        out = O.dynamics_step(c["state"], c["control"], c["dt"], c["friction"])
+        np.testing.assert_allclose(out, np.asarray(c["next"], F32), rtol=0, atol=1e-7)
+    hp = np.pi / 2   # interact_drive/tests/test_simulation_utils.py:113-158
+    np.testing.assert_allclose(O.dynamics_step([0, 0, 1, hp], [0, 0], 1.0, 0.0), [0, 1, 1, hp], atol=1e-6)
+    np.testing.assert_allclose(O.dynamics_step([0, 0, 1, hp], [0, 0], 1.0, 1.0), [0, 0.5, 0, hp], atol=1e-6)
+    np.testing.assert_allclose(O.dynamics_step([0, 0, 1, hp], [0, 0], 1.0, 0.5), [0, 0.75, 0.5, hp], atol=1e-6)
+    np.testing.assert_allclose(O.dynamics_step([0, 0, 1, 0], [0, 0], 1.0, 0.5), [0.75, 0, 0.5, 0], atol=1e-6)
+
+
+def test_smooth_helpers_doctests_and_golden():
+    g = load_golden("primitives.json")
+    assert O.smooth_f(0.0) == 0.0 and O.smooth_f(1.0) > 0 and abs(O.smooth_f(1e10) - 1) < 1e-7
+    assert O.smooth_threshold(0.0, 0.0, 1.0) == 1.0 and O.smooth_threshold(-1.0, 0.0, 1.0) == 0.0
+    assert abs(O.smooth_threshold(-0.5, 0.0, 1.0) - 0.5) < 1e-7
+    assert O.smooth_bump(0.0, -1.0, 1.0) == 1.0 and O.smooth_bump(1.0, -1.0, 1.0) == 0.0 and \
+        O.smooth_bump(-1.0, -1.0, 1.0) == 0.0 and O.smooth_bump(0.5, -1.0, 1.0) > 0
+    for k, v in g["f_doctest"].items():
+        assert abs(O.smooth_f(float(k[2:-1])) - v) <= 1e-7
+    for c in g["f"]:
+        assert abs(O.smooth_f(c["x"], c["shape"]) - c["y"]) <= 2e-7 * max(1, abs(c["y"]))
+    for c in g["threshold"]:
+        assert abs(O.smooth_threshold(c["z"], c["threshold"], c["width"]) - c["y"]) <= 5e-7
+    for c in g["bump"]:
+        assert abs(O.smooth_bump(c["z"], c["start"], c["end"]) - c["y"]) <= 5e-7
+
+
+def test_features_golden():
+    for c in load_golden("features.json")["cases"]:
+        phi = O.features(_params(c), np.asarray(c["state"], F32))
+        np.testing.assert_allclose(phi, np.asarray(c["phi"], F32), rtol=2e-6, atol=2e-7)
+
+
+def test_mpc_reward_and_gradient_golden():
+    """Value and d/d controls against the reference's mpc_reward under autograd."""
+    for c in load_golden("mpc_reward.json")["cases"]:
+        p = _params(c, H=c["H"], other_mode=c["other_mode"], friction=c["friction"], dt=c["dt"])
+        R, G = O.mpc_reward(p, c["init_state"], c["controls"], c["weights"], other_controls=c["other_controls"])
+        gref = np.asarray(c["grad"], F32)
+        assert abs(R - c["R"]) <= 2e-6 * max(1.0, abs(c["R"]))
+        assert np.max(np.abs(G - gref)) <= 2e-6 * max(1.0, np.abs(gref).max())
+
+
+def test_adjoint_against_finite_differences_f64():
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        C, H = int(rng.integers(2, 5)), int(rng.integers(3, 9))
+        lanes = (-0.1, 0.0, 0.1) if trial % 2 else (-0.05, 0.05)
+        p = O.OracleParams(H=H, C=C, lane_x=lanes, num_lanes=len(lanes), other_mode=trial % 3 == 0)
+        world = np.zeros((C, 4))
+        world[:, 0] = rng.uniform(-0.12, 0.12, C)
+        world[:, 1] = rng.uniform(-1, -0.6, C)
+        world[:, 2] = rng.uniform(0.4, 1.2, C)
+        world[:, 3] = np.pi / 2 + rng.uniform(-0.3, 0.3, C)
+        u = rng.normal(size=(H, 2)) * [1.0, 1.5]
+        w = rng.normal(size=p.K)
+        oc = rng.normal(size=(C - 1, H, 2)) if p.other_mode else None
+        R, G = O.mpc_reward(p, world, u, w, other_controls=oc, dtype=np.float64)
+        eps = 1e-6
+        for (t, k) in ((0, 0), (H - 1, 1), (H // 2, 0), (H // 2, 1)):
+            up, um = u.copy(), u.copy()
+            up[t, k] += eps
+            um[t, k] -= eps
+            fd = (O.mpc_reward(p, world, up, w, other_controls=oc, dtype=np.float64, grad=False)
+                  - O.mpc_reward(p, world, um, w, other_controls=oc, dtype=np.float64, grad=False)) / (2 * eps)
+            assert abs(fd - G[t, k]) <= 1e-5 * max(1.0, abs(fd)), (trial, t, k, fd, G[t, k])
+
+
+def test_clip_masks_follow_tensorflow():
+    """d clip / d u = 1 on the closed interval: at the bound the gradient passes,
+    beyond it it is exactly zero."""
+    p = O.OracleParams(H=3, C=2)
+    world = np.array([[0.02, -0.9, 0.8, np.pi / 2], [0.0, -0.6, 0.5, np.pi / 2]], F32)
+    w = np.array([-0.5, 0.1, 0.2, 0.3, -0.2, -0.5, -0.5], F32)
+    u = np.array([[4.0, 4.0], [4.5, -4.5], [-8.0, -4.0]], F32)
+    _, G = O.mpc_reward(p, world, u, w)
+    assert G[1, 0] == 0 and G[1, 1] == 0
+    assert G[0, 0] != 0 and G[2, 0] != 0 and G[2, 1] != 0
+
+
+def test_planner_known_answers():
+    """interact_drive/planner/tests/test_naivePlanner.py:21-32, :50-63 (atol 1e-5 there)."""
+    for c in load_golden("planner_kats.json")["cases"]:
+        p = O.OracleParams(H=c["horizon"], C=2, n_iter=c["n_iter"], lr=c["learning_rate"], friction=c["friction"])
+        world = np.asarray([c["init_state"], [50.0, 50.0, 0.0, np.pi / 2]], F32)
+        r = O.generate_plan(p, world, [-1, 0, 0, 0, 0, 0, 0])
+        np.testing.assert_allclose(r["plan"], np.asarray(c["expected"]), atol=1e-5)
+        np.testing.assert_allclose(r["plan"], np.asarray(c["plan"]), atol=1e-6)
+
+
+def test_generate_plan_golden_scenarios():
+    for c in load_golden("plans.json")["cases"]:
+        spec = O.scenario_params(c["scenario"])
+        oc = None
+        if spec.params.other_mode == 1:
+            sc = spec.scenario
+            oc = [[(sc.plan[j][t] if t < len(sc.plan[j]) else sc.control[j]) for t in range(spec.params.H)]
+                  for j in range(spec.params.C - 1)]
+        r = O.generate_plan(spec.params, c["world_state"], c["weights_normalised"], other_controls=oc)
+        np.testing.assert_allclose(r["plan"], np.asarray(c["plan"], F32), atol=5e-6)
+        np.testing.assert_allclose(r["plan"][0], np.asarray(c["control"], F32), atol=5e-6)
+
+
+EPISODES = ["episode_finite_horizon_true_full.json", "episode_finite_horizon_tuned_full.json",
+            "episode_finite_horizon_true_extra_inits.json", "episode_finite_horizon_true_h6.json",
+            "episode_local_opt_true_full.json", "episode_local_opt_tuned_full.json",
+            "episode_local_opt_scaled_short.json", "episode_local_opt_true_extra_inits.json",
+            "episode_replanning_true_full.json", "episode_replanning_tuned_full.json"]
+
+
+@pytest.mark.parametrize("fname", EPISODES)
+def test_episode_golden(fname):
+    e = load_golden(fname)
+    spec = O.scenario_params(e["scenario"], horizon=e["horizon"], extra_inits=e["extra_inits"])
+    assert spec.params.n_iter == e["n_iter"]
+    for smp in e["samples"]:
+        r = O.episode(spec.params, spec.scenario, np.asarray(e["init"], F32), e["plan_weights"], e["true_weights"],
+                      e["T"], unlucky_idx=smp["unlucky_car_idx"])
+        assert abs(r["ret"] - smp["return"]) <= 2e-6 * abs(smp["return"])
+        np.testing.assert_allclose(r["controls"], np.asarray(smp["controls"], F32), atol=5e-6)
+        np.testing.assert_allclose(r["states"][:, 0], np.asarray(smp["robot_states"], F32), atol=5e-6)
+        for j, os_ in enumerate(smp["other_states"]):
+            np.testing.assert_allclose(r["states"][:, j + 1], np.asarray(os_, F32), atol=2e-6)
+
+
+def test_survey_cross_check_returns():
+    """a second, independent reading of the reference gave these returns."""
+    want = {"finite_horizon": [-0.04167331475764513], "local_opt": [-0.6909196190536022],
+            "replanning": [-1.0614905506372452, -0.16572473291307688]}
+    for name, rets in want.items():
+        spec = O.scenario_params(name)
+        w = spec.designer_weights / np.linalg.norm(spec.designer_weights)
+        for k, ret in enumerate(rets):
+            r = O.episode(spec.params, spec.scenario, spec.example_init, w, w, spec.eval_horizon, unlucky_idx=k + 1)
+            assert abs(r["ret"] - ret) <= 5e-6 * abs(ret)
+
+
+def test_batch_entry_points_match_scalar_ones():
+    spec = O.scenario_params("replanning")
+    w = (spec.designer_weights / np.linalg.norm(spec.designer_weights)).astype(F32)
+    ri = np.tile(spec.example_init, (6, 1)).astype(F32)
+    ri[:, 0] += np.linspace(-0.003, 0.003, 6, dtype=F32)
+    ul = np.array([1, 2, 1, 2, 1, 2], np.int32)
+    batch = O.episode_batch(spec.params, spec.scenario, ri, w, w, 8, unlucky_idx=ul)
+    for b in range(6):
+        one = O.episode(spec.params, spec.scenario, ri[b], w, w, 8, unlucky_idx=int(ul[b]))
+        assert batch[b] == one["ret"]
