@@ -343,25 +343,31 @@ int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc, const float *
 }
 
 // ---- host-buffer layer ------------------------------------------------------------------------
+static constexpr int kCtxStreams = 3;
+static constexpr int kMaxChunks = 16;
+
 struct ocd_ctx {
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;                 // small calls (episodes)
+    cudaStream_t lanes[kCtxStreams];     // the chunk pipeline of ocd_solve_batch_host
+    cudaEvent_t ready;                   // shared inputs (weights) are on the device
+    cudaEvent_t done[kMaxChunks];        // chunk c's outputs are in host memory
     char *dev;      size_t dev_cap;
     char *pin;      size_t pin_cap;
 };
 
-static int ctx_reserve(ocd_ctx *c, size_t bytes) {
-    if (bytes > c->dev_cap) {
+static int ctx_reserve(ocd_ctx *c, size_t dev_bytes, size_t pin_bytes) {
+    if (dev_bytes > c->dev_cap) {
         if (c->dev) cudaFree(c->dev);
         c->dev = nullptr; c->dev_cap = 0;
-        if (cudaMalloc((void **)&c->dev, bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
-        c->dev_cap = bytes;
+        if (cudaMalloc((void **)&c->dev, dev_bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
+        c->dev_cap = dev_bytes;
     }
-    if (bytes > c->pin_cap) {
+    if (pin_bytes > c->pin_cap) {
         if (c->pin) cudaFreeHost(c->pin);
         c->pin = nullptr; c->pin_cap = 0;
-        if (cudaMallocHost((void **)&c->pin, bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
-        c->pin_cap = bytes;
+        if (cudaMallocHost((void **)&c->pin, pin_bytes) != cudaSuccess) { cudaGetLastError(); return OCD_ENOMEM; }
+        c->pin_cap = pin_bytes;
     }
     return OCD_OK;
 }
@@ -374,7 +380,14 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
     ocd_ctx *c = new (std::nothrow) ocd_ctx();
     if (!c) return OCD_ENOMEM;
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < kCtxStreams; ++i)
+        ok = ok && cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kMaxChunks; ++i)
+        ok = ok && cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
         delete c;
         return OCD_ECUDA;
     }
@@ -388,11 +401,13 @@ void ocd_ctx_destroy(ocd_ctx *c) {
     if (c->dev) cudaFree(c->dev);
     if (c->pin) cudaFreeHost(c->pin);
     cudaStreamDestroy(c->stream);
+    for (int i = 0; i < kCtxStreams; ++i) cudaStreamDestroy(c->lanes[i]);
+    cudaEventDestroy(c->ready);
+    for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(c->done[i]);
     delete c;
 }
 
-// a tiny bump allocator over the ctx buffers: every array gets the same offset on the pinned
-// and on the device side, so one memcpy each way moves all inputs / all outputs.
+// a tiny bump allocator over the ctx buffers
 struct Arena {
     size_t off = 0;
     size_t take(size_t bytes) {
@@ -402,47 +417,145 @@ struct Arena {
     }
 };
 
+// true when `ptr` is page-locked host memory the copy engines can read or write directly
+static bool is_pinned(const void *ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// One [rows][B] host array moved in column chunks.  Pinned user memory is copied in place (a
+// strided 2-D copy); pageable memory goes through the context's pinned staging area.
+struct HostArray {
+    char  *user;        // host array [rows][B] of `elem`-byte items (null: absent)
+    int    rows;
+    size_t elem;
+    bool   pinned;
+    size_t dev_off, pin_off;    // per-chunk compact [rows][n] buffers in the device / pinned arena
+};
+
+static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk,
+                     cudaStream_t st) {
+    if (!a.user) return OCD_OK;
+    char *dst = c->dev + a.dev_off + (size_t)chunk * a.rows * cap * a.elem;
+    cudaError_t e;
+    if (a.pinned) {
+        e = cudaMemcpy2DAsync(dst, n * a.elem, a.user + b0 * a.elem, B * a.elem, n * a.elem, a.rows,
+                              cudaMemcpyHostToDevice, st);
+    } else {
+        char *stage = c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem;
+        for (int r = 0; r < a.rows; ++r)
+            std::memcpy(stage + (size_t)r * n * a.elem, a.user + ((size_t)r * B + b0) * a.elem, n * a.elem);
+        e = cudaMemcpyAsync(dst, stage, (size_t)a.rows * n * a.elem, cudaMemcpyHostToDevice, st);
+    }
+    return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
+}
+
+static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk,
+                     cudaStream_t st) {
+    const char *src = c->dev + a.dev_off + (size_t)chunk * a.rows * cap * a.elem;
+    cudaError_t e;
+    if (a.pinned)
+        e = cudaMemcpy2DAsync(a.user + b0 * a.elem, B * a.elem, src, n * a.elem, n * a.elem, a.rows,
+                              cudaMemcpyDeviceToHost, st);
+    else
+        e = cudaMemcpyAsync(c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem, src,
+                            (size_t)a.rows * n * a.elem, cudaMemcpyDeviceToHost, st);
+    return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
+}
+
+static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk) {
+    if (a.pinned) return;
+    const char *stage = c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem;
+    for (int r = 0; r < a.rows; ++r)
+        std::memcpy(a.user + ((size_t)r * B + b0) * a.elem, stage + (size_t)r * n * a.elem, n * a.elem);
+}
+
+// The batch is cut into column chunks that flow through three streams: while chunk i is being
+// solved, chunk i+1 is on its way to the device and chunk i-1 on its way back, so that the call
+// costs about max(copy, solve) instead of their sum.
 int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
                          int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
                          const float *cur_speed, float *plan, float *losses, int32_t *best, int64_t B) {
     KParams k;
     int rc = digest(p, k);
     if (rc) return rc;
+    if (B == 0) return OCD_OK;
     if (!c || !world || !plan || !losses || !best || B < 0) return OCD_EINVAL;
     if ((rc = check_weights(weights, Bw, weight_idx, B))) return rc;
     if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
-    if (B == 0) return OCD_OK;
     if (cudaSetDevice(c->device) != cudaSuccess) return OCD_ECUDA;
     const int C = k.NO + 1;
-    Arena ar;
-    const size_t n_world = sizeof(float) * C * 4 * B, o_world = ar.take(n_world);
-    const size_t n_w = sizeof(float) * k.K * Bw, o_w = ar.take(n_w);
-    const size_t n_idx = weight_idx ? sizeof(int32_t) * B : 0, o_idx = ar.take(n_idx);
-    const size_t n_oc = k.other_mode == 1 ? sizeof(float) * k.NO * k.H * 2 * Bo : 0, o_oc = ar.take(n_oc);
-    const size_t n_cs = cur_speed ? sizeof(float) * B : 0, o_cs = ar.take(n_cs);
-    const size_t in_end = ar.off;
-    const size_t n_plan = sizeof(float) * k.H * 2 * B, o_plan = ar.take(n_plan);
-    const size_t n_loss = sizeof(float) * k.S * B, o_loss = ar.take(n_loss);
-    const size_t n_best = sizeof(int32_t) * B, o_best = ar.take(n_best);
-    if ((rc = ctx_reserve(c, ar.off))) return rc;
-    std::memcpy(c->pin + o_world, world, n_world);
-    std::memcpy(c->pin + o_w, weights, n_w);
-    if (n_idx) std::memcpy(c->pin + o_idx, weight_idx, n_idx);
-    if (n_oc) std::memcpy(c->pin + o_oc, other_controls, n_oc);
-    if (n_cs) std::memcpy(c->pin + o_cs, cur_speed, n_cs);
-    if (cudaMemcpyAsync(c->dev, c->pin, in_end, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return OCD_ECUDA;
-    rc = ocd_solve_batch(p, (const float *)(c->dev + o_world), n_oc ? (const float *)(c->dev + o_oc) : nullptr, Bo,
-                         (const float *)(c->dev + o_w), Bw, n_idx ? (const int32_t *)(c->dev + o_idx) : nullptr,
-                         n_cs ? (const float *)(c->dev + o_cs) : nullptr, (float *)(c->dev + o_plan),
-                         (float *)(c->dev + o_loss), (int32_t *)(c->dev + o_best), nullptr, B, c->stream);
-    if (rc) return rc;
-    if (cudaMemcpyAsync(c->pin + o_plan, c->dev + o_plan, ar.off - o_plan, cudaMemcpyDeviceToHost, c->stream) !=
-        cudaSuccess)
-        return OCD_ECUDA;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
-    std::memcpy(plan, c->pin + o_plan, n_plan);
-    std::memcpy(losses, c->pin + o_loss, n_loss);
-    std::memcpy(best, c->pin + o_best, n_best);
+    const bool per_problem_w = !weight_idx && Bw == B && B > 1;     // weights travel with the chunks
+    const bool per_problem_oc = k.other_mode == 1 && Bo == B && B > 1;
+
+    int nchunks = (int)((B + 65535) / 65536);
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    const int64_t cap = (((B + nchunks - 1) / nchunks) + 63) / 64 * 64;      // problems per chunk
+    nchunks = (int)((B + cap - 1) / cap);
+
+    HostArray a_world{(char *)world, C * 4, 4, is_pinned(world), 0, 0};
+    HostArray a_idx{(char *)weight_idx, 1, 4, is_pinned(weight_idx), 0, 0};
+    HostArray a_w{per_problem_w ? (char *)weights : nullptr, k.K, 4, is_pinned(weights), 0, 0};
+    HostArray a_oc{per_problem_oc ? (char *)other_controls : nullptr, k.NO * k.H * 2, 4, is_pinned(other_controls), 0, 0};
+    HostArray a_cs{(char *)cur_speed, 1, 4, is_pinned(cur_speed), 0, 0};
+    HostArray a_plan{(char *)plan, k.H * 2, 4, is_pinned(plan), 0, 0};
+    HostArray a_loss{(char *)losses, k.S, 4, is_pinned(losses), 0, 0};
+    HostArray a_best{(char *)best, 1, 4, is_pinned(best), 0, 0};
+    HostArray *arrays[] = {&a_world, &a_idx, &a_w, &a_oc, &a_cs, &a_plan, &a_loss, &a_best};
+    Arena dev, pin;
+    for (HostArray *a : arrays)
+        if (a->user) {
+            a->dev_off = dev.take((size_t)nchunks * a->rows * cap * a->elem);
+            if (!a->pinned) a->pin_off = pin.take((size_t)nchunks * a->rows * cap * a->elem);
+        }
+    // shared (not per-problem) inputs: copied once, in full
+    const size_t n_w = per_problem_w ? 0 : sizeof(float) * k.K * Bw, o_w = dev.take(n_w), s_w = pin.take(n_w);
+    const size_t n_oc = (k.other_mode == 1 && !per_problem_oc) ? sizeof(float) * k.NO * k.H * 2 * Bo : 0;
+    const size_t o_oc = dev.take(n_oc), s_oc = pin.take(n_oc);
+    if ((rc = ctx_reserve(c, dev.off, pin.off))) return rc;
+    if (n_w) std::memcpy(c->pin + s_w, weights, n_w);
+    if (n_oc) std::memcpy(c->pin + s_oc, other_controls, n_oc);
+    cudaStream_t s0 = c->lanes[0];
+    if (n_w && cudaMemcpyAsync(c->dev + o_w, c->pin + s_w, n_w, cudaMemcpyHostToDevice, s0) != cudaSuccess) return OCD_ECUDA;
+    if (n_oc && cudaMemcpyAsync(c->dev + o_oc, c->pin + s_oc, n_oc, cudaMemcpyHostToDevice, s0) != cudaSuccess) return OCD_ECUDA;
+    if (cudaEventRecord(c->ready, s0) != cudaSuccess) return OCD_ECUDA;
+
+    auto chunk_ptr = [&](const HostArray &a, int ch) -> char * {
+        return a.user ? c->dev + a.dev_off + (size_t)ch * a.rows * cap * a.elem : nullptr;
+    };
+    for (int ch = 0; ch < nchunks && rc == OCD_OK; ++ch) {
+        const int64_t b0 = (int64_t)ch * cap, n = (b0 + cap <= B) ? cap : B - b0;
+        cudaStream_t st = c->lanes[ch % kCtxStreams];
+        if (cudaStreamWaitEvent(st, c->ready, 0) != cudaSuccess) { rc = OCD_ECUDA; break; }
+        for (HostArray *a : {&a_world, &a_idx, &a_w, &a_oc, &a_cs})
+            if (rc == OCD_OK) rc = h2d_chunk(c, *a, B, b0, n, cap, ch, st);
+        if (rc) break;
+        rc = ocd_solve_batch(p, (const float *)chunk_ptr(a_world, ch),
+                             per_problem_oc ? (const float *)chunk_ptr(a_oc, ch) : (n_oc ? (const float *)(c->dev + o_oc) : nullptr),
+                             per_problem_oc ? n : Bo,
+                             per_problem_w ? (const float *)chunk_ptr(a_w, ch) : (const float *)(c->dev + o_w),
+                             per_problem_w ? n : Bw, (const int32_t *)chunk_ptr(a_idx, ch),
+                             (const float *)chunk_ptr(a_cs, ch), (float *)chunk_ptr(a_plan, ch),
+                             (float *)chunk_ptr(a_loss, ch), (int32_t *)chunk_ptr(a_best, ch), nullptr, n, st);
+        for (HostArray *a : {&a_plan, &a_loss, &a_best})
+            if (rc == OCD_OK) rc = d2h_chunk(c, *a, B, b0, n, cap, ch, st);
+        if (rc == OCD_OK && cudaEventRecord(c->done[ch], st) != cudaSuccess) rc = OCD_ECUDA;
+    }
+    if (rc) {
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        return rc;
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (cudaEventSynchronize(c->done[ch]) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
+        const int64_t b0 = (int64_t)ch * cap, n = (b0 + cap <= B) ? cap : B - b0;
+        for (HostArray *a : {&a_plan, &a_loss, &a_best}) unstage_chunk(c, *a, B, b0, n, cap, ch);
+    }
     return OCD_OK;
 }
 
@@ -466,7 +579,7 @@ int ocd_episode_batch_host(ocd_ctx *c, const ocd_params *p, const ocd_scenario *
     const size_t n_ul = unlucky_idx ? sizeof(int32_t) * B : 0, o_ul = ar.take(n_ul);
     const size_t in_end = ar.off;
     const size_t n_ret = sizeof(float) * B, o_ret = ar.take(n_ret);
-    if ((rc = ctx_reserve(c, ar.off))) return rc;
+    if ((rc = ctx_reserve(c, ar.off, ar.off))) return rc;
     std::memcpy(c->pin + o_ri, robot_init, n_ri);
     if (n_oi) std::memcpy(c->pin + o_oi, other_init, n_oi);
     std::memcpy(c->pin + o_w, plan_weights, n_w);

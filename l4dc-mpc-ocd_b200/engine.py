@@ -373,9 +373,22 @@ class HostContext:
         except Exception:
             pass
 
+    @staticmethod
+    def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+        """A page-locked host array: the copy engines read / write it in place, so the host-buffer
+        calls skip their staging copies (pageable arrays work too, through a pinned staging area)."""
+        t = torch.empty(tuple(shape), dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.int32,
+                        pin_memory=True)
+        a = t.numpy()
+        HostContext._keepalive[a.ctypes.data] = t
+        return a
+
+    _keepalive: dict = {}
+
     def solve_soa(self, p: PlannerParams, world: np.ndarray, weights: np.ndarray, weight_idx=None,
-                  other_controls=None, cur_speed=None):
-        """Host SoA arrays: world [C][4][B], weights [K][Bw] -> plan [H][2][B], losses [S][B], best [B]."""
+                  other_controls=None, cur_speed=None, out=None):
+        """Host SoA arrays: world [C][4][B], weights [K][Bw] -> plan [H][2][B], losses [S][B], best [B].
+        `out` may hold preallocated (ideally pinned) plan / losses / best arrays."""
         world = np.ascontiguousarray(world, np.float32)
         weights = np.ascontiguousarray(weights, np.float32)
         B, Bw = world.shape[-1], weights.shape[-1]
@@ -383,9 +396,14 @@ class HostContext:
         oc = None if other_controls is None else np.ascontiguousarray(other_controls, np.float32)
         Bo = 0 if oc is None else oc.shape[-1]
         cs = None if cur_speed is None else np.ascontiguousarray(cur_speed, np.float32)
-        plan = np.empty((p.H, 2, B), np.float32)
-        losses = np.empty((p.S, B), np.float32)
-        best = np.empty((B,), np.int32)
+        if out is None:
+            out = dict(plan=np.empty((p.H, 2, B), np.float32), losses=np.empty((p.S, B), np.float32),
+                       best=np.empty((B,), np.int32))
+        plan, losses, best = out["plan"], out["losses"], out["best"]
+        if plan.shape != (p.H, 2, B) or losses.shape != (p.S, B) or best.shape != (B,) or \
+                plan.dtype != np.float32 or losses.dtype != np.float32 or best.dtype != np.int32 or \
+                not (plan.flags.c_contiguous and losses.flags.c_contiguous and best.flags.c_contiguous):
+            raise ValueError("out arrays must be C-contiguous plan [H,2,B] f32, losses [S,B] f32, best [B] i32")
         ps = p.c_struct()
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         rc = N.lib.ocd_solve_batch_host(self._h, C.addressof(ps), vp(world), vp(oc), Bo, vp(weights), Bw, vp(idx),
