@@ -172,6 +172,15 @@ static int digest(const ocd_params *p, KParams &k) {
     k.fshape = (float)(5.0 / 0.05);
     k.turn = (float)(5 * 0.13);                  // naive_planner.py:109-110
     for (int i = 0; i < p->L; ++i) k.lane_x[i] = (float)p->lane_x[i];
+    {   // midpoints between lanes adjacent in sorted order (the only places where the lane-min can tie)
+        float sorted[OCD_MAX_LANES];
+        for (int i = 0; i < p->L; ++i) sorted[i] = k.lane_x[i];
+        for (int i = 1; i < p->L; ++i)
+            for (int j = i; j > 0 && sorted[j] < sorted[j - 1]; --j) {
+                const float t = sorted[j]; sorted[j] = sorted[j - 1]; sorted[j - 1] = t;
+            }
+        for (int i = 0; i + 1 < p->L; ++i) k.lane_mid[i] = (float)(((double)sorted[i] + (double)sorted[i + 1]) * 0.5);
+    }
     return OCD_OK;
 }
 
@@ -182,10 +191,7 @@ static int check_weights(const float *weights, long long Bw, const int32_t *idx,
     return OCD_OK;
 }
 
-static int pick_P(long long B) {
-    // 64 problems per block once that still gives every SM several blocks; 32 below that
-    return B >= 64LL * 148 * 4 ? 64 : 32;
-}
+static int pick_P(long long) { return kP; }
 
 // (H, other cars, lanes) specialisations: the shipped scenarios; everything else takes the
 // runtime-shape kernels.

@@ -40,6 +40,7 @@ struct KParams {
     float thr_lo, thr_w, fshape;  // fence ramp: |x| in [thr_lo, thr_lo + thr_w], shape = 5/width
     float turn;                   // 5*0.13 start angular velocity
     float lane_x[OCD_MAX_LANES];
+    float lane_mid[OCD_MAX_LANES];  // midpoints between lanes adjacent in sorted order: where the lane-min ties
 };
 
 // collision bump half-widths (merging.py:70-73) and their reciprocals
@@ -239,10 +240,9 @@ __device__ __forceinline__ GradW make_gradw(const KParams &k, const float *w /*[
 }
 
 // d/dx of min_i 10 (x - l_i)^2, divided by 20: the offset to the nearest lane, averaged over
-// exact ties (TF reduce_min splits the gradient evenly).  Ties are found on the feature values
-// themselves, as the reference does; the averaging runs only when one occurred.
-template <int LT, bool PRECISE>
-__device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
+// exact ties of the feature values (TF reduce_min splits the gradient evenly).
+template <int LT>
+__device__ __forceinline__ float lane_min_offset_exact(const KParams &k, float x) {
     const int L = LT > 0 ? LT : k.L;
     float dsel = x - k.lane_x[0];
     float fm = (dsel * dsel) * 10.0f;
@@ -256,9 +256,7 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
             dsel = (f < fm) ? d : dsel;
             fm = fminf(fm, f);
         }
-    // rare: an earlier tie may have been beaten later, so recount against the minimum.  FAST asks
-    // the whole warp first, so that the common case is one uniform branch.
-    if (PRECISE ? tie : __any_sync(OCD_FULL, tie)) {
+    if (tie) {   // rare: an earlier tie may have been beaten later, so recount against the minimum
         float sum = 0.0f, cnt = 0.0f;
         for (int i = 0; i < L; ++i) {
             const float d = x - k.lane_x[i];
@@ -267,8 +265,30 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
                 cnt += 1.0f;
             }
         }
-        dsel = (tie && cnt > 1.0f) ? __fdiv_rn(sum, cnt) : dsel;
+        dsel = (cnt > 1.0f) ? __fdiv_rn(sum, cnt) : dsel;
     }
+    return dsel;
+}
+
+// FAST: the nearest lane by |x - l_i| (no feature values needed); feature values can only tie when
+// x sits within rounding of a midpoint between two neighbouring lanes, and only then -- decided by a
+// warp vote, so normally one uniform branch -- the exact rule above runs.
+template <int LT, bool PRECISE>
+__device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
+    if (PRECISE) return lane_min_offset_exact<LT>(k, x);
+    const int L = LT > 0 ? LT : k.L;
+    float dsel = x - k.lane_x[0];
+    float near = 1.0f;
+#pragma unroll
+    for (int i = 1; i < (LT > 0 ? LT : OCD_MAX_LANES); ++i)
+        if (i < L) {
+            const float d = x - k.lane_x[i];
+            dsel = (fabsf(d) < fabsf(dsel)) ? d : dsel;
+            near = fminf(near, fabsf(x - k.lane_mid[i - 1]));
+        }
+    const bool close = near < 1e-6f;
+    if (__any_sync(OCD_FULL, close))
+        if (close) dsel = lane_min_offset_exact<LT>(k, x);
     return dsel;
 }
 

@@ -20,7 +20,8 @@
 
 namespace ocd {
 
-static constexpr int kMaxThreads = 384;   // S=6 starts x P=64 problems
+static constexpr int kP = 32;             // problems per block: one warp per start
+static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
 // ---------------------------------------------------------------------------------------------
 // argument blocks (passed by value as kernel parameters)
@@ -115,7 +116,7 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 template <int HT, int NOT_, int LT, bool PRECISE>
 __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ float smem_raw[];
-    const int P = a.P;
+    constexpr int P = kP;     // compile-time, so every slab access is base + immediate
     const Smem m = carve(smem_raw, k, P, false);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
@@ -184,7 +185,7 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 __global__ void __launch_bounds__(kMaxThreads)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ float smem_raw[];
-    const int P = a.P;
+    constexpr int P = kP;
     const Smem m = carve(smem_raw, k, P, true);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
