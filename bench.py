@@ -102,12 +102,21 @@ def _visible_index(local_rank: int) -> int:
 
 
 # ---------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1; the oracle's OpenMP loop
+    takes its thread count as an argument, so that default does not throttle the CPU arm.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_arm(problems: int, threads: int | None = None, seed: int = 1234):
     """Times the CPU oracle (oracle/: C restatement of the reference's planner, OpenMP over
     problems) on `problems` synthetic problems of the bench shape.  -> (solves/s, seconds, threads)"""
     import oracle as O
     from l4dc_mpc_ocd_b200 import synthetic
-    threads = threads or O.max_threads()
+    threads = threads or host_threads()
     batch = synthetic.make_batch(problems, seed=seed)
     w = batch["weights"][batch["weight_idx"]]
     p = O.OracleParams()
@@ -123,8 +132,7 @@ def reference_main(args, rank: int, world_size: int):
     oracle port of NaivePlanner.generate_plan, all host threads (cpu_baseline.kind = "port")."""
     if rank != 0:
         return
-    import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     rate, _, _ = cpu_arm(max(256, 32 * threads), threads)          # calibrate
     per_step = int(max(256, min(rate * 1.5, 2_000_000)))           # about 1.5 s of CPU work per step
     for _ in range(args.warmup):
@@ -313,8 +321,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------
     if not args.no_extras and world_size == 1:
-        import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         rate, _, _ = cpu_arm(max(256, 32 * threads), threads)
         n = int(max(512, min(rate * 12.0, 4_000_000)))         # about 12 s of CPU work
         v, dt, _ = cpu_arm(n, threads)

@@ -73,6 +73,23 @@ def run_opt(env, init_states, args, optimization_seed, verbose=True):
     return mpc_ord
 
 
+def _init_distributed():
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL process group.  -> rank or None."""
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    from ..runtime import set_default_device
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    set_default_device(local)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank()
+
+
 def main(argv=None):
     parser = ArgumentParser()
     parser.add_argument('scenario', type=str, choices=['local_opt', 'finite_horizon', 'replanning'],
@@ -97,6 +114,17 @@ def main(argv=None):
         args.one_by_one = False
     env = envs[args.scenario]
     optimization_seed = np.random.randint(0, 2 ** 32) if args.opt_seed is None else args.opt_seed
+    rank = _init_distributed()
+    if rank is not None:
+        # every rank runs the same optimiser on the same (all-gathered) returns: share the seed, and
+        # let rank 0 alone talk and write the history
+        import torch
+        import torch.distributed as dist
+        seed_t = torch.tensor([optimization_seed], dtype=torch.int64, device="cuda")
+        dist.broadcast(seed_t, 0)
+        optimization_seed = int(seed_t.item())
+        if rank != 0:
+            args.quiet, args.no_save = True, True
     if args.seed is None:
         args.seed = optimization_seed
     env_seeds = [(args.seed * 1000000 + i) % (2 ** 32) for i in range(args.n_inits)]
