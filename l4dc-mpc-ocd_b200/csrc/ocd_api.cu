@@ -25,7 +25,10 @@ namespace ocd {
 OCD_EXTERN(5, 1, 3)   // finite_horizon, local_opt, the bench shape
 OCD_EXTERN(5, 2, 2)   // replanning
 OCD_EXTERN(6, 1, 3)   // finite_horizon validation (H=6, n_iter=200)
-OCD_EXTERN(0, 0, 0)   // any other shape: runtime H, cars, lanes
+OCD_EXTERN(5, 0, 3)   // H=5 on three lanes with any number of other cars (sweep)
+OCD_EXTERN(0, 1, 3)   // any horizon, one other car, three lanes: segmented adjoint (sweep H=15, 50)
+OCD_EXTERN(0, 0, 3)   // any horizon / cars on three lanes: segmented adjoint
+OCD_EXTERN(0, 0, 0)   // any other shape: runtime H, cars, lanes (segmented adjoint)
 #undef OCD_EXTERN
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +203,9 @@ static int pick_P(long long) { return kP; }
         if (k.H == 5 && k.NO == 1 && k.L == 3) return FN<5, 1, 3, PRECISE>(__VA_ARGS__);    \
         if (k.H == 5 && k.NO == 2 && k.L == 2) return FN<5, 2, 2, PRECISE>(__VA_ARGS__);    \
         if (k.H == 6 && k.NO == 1 && k.L == 3) return FN<6, 1, 3, PRECISE>(__VA_ARGS__);    \
+        if (k.H == 5 && k.L == 3) return FN<5, 0, 3, PRECISE>(__VA_ARGS__);                 \
+        if (k.NO == 1 && k.L == 3) return FN<0, 1, 3, PRECISE>(__VA_ARGS__);                \
+        if (k.L == 3) return FN<0, 0, 3, PRECISE>(__VA_ARGS__);                             \
         return FN<0, 0, 0, PRECISE>(__VA_ARGS__);                                           \
     } while (0)
 

@@ -294,10 +294,14 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
 
 // Gradient of w.phi with respect to the robot state (x, y, v, th) at one world state.
 //   oth: other cars' slab coordinates, x of car j at oth[j*jstride], y at oth[j*jstride + cstride].
-template <int NOT_, int LT, bool PRECISE>
+// LIN (FAST, constant-velocity other cars only): instead of a position per horizon step the slab holds
+// (x0, dx, y0, dy) per car -- four rows, car stride jstride = 4*cstride -- and the position after
+// tf steps is x0 + tf*dx.  That keeps the slab independent of H, which is what lets long horizons with
+// many cars keep several blocks per SM.
+template <int NOT_, int LT, bool PRECISE, bool LIN = false>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
-                                             float &gx, float &gy, float &gv, float &gth) {
+                                             float &gx, float &gy, float &gv, float &gth, float tf = 0.0f) {
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
     // speed: min((v sin th - ts)^2, 4 ts^2)                                  merging.py:58-59
     {
@@ -338,10 +342,16 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         // hx, hy below are d(val)/d(position) without the constant -2/half-width (folded into
         // wcx, wcy).  A warp with every lane outside every support skips the transcendental part.
         float best = 0.0f, hx = 0.0f, hy = 0.0f, cnt = 1.0f;
-#pragma unroll(NOT_ > 0 ? NOT_ : 1)
-        for (int j = 0; j < NO; ++j) {
-            const float nx = fmaf(x, OCD_BUMP_IX, -oth[j * jstride]);
-            const float ny = fmaf(y, OCD_BUMP_IY, -oth[j * jstride + cstride]);
+        // runtime car count: fully unrolled with uniform guards, so that every slab address is an
+        // immediate and no loop counter is carried
+#pragma unroll
+        for (int j = 0; j < (NOT_ > 0 ? NOT_ : OCD_MAX_OTHER); ++j) {
+            if (NOT_ == 0 && j >= NO) break;
+            const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
+            const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
+                                  : oth[j * jstride + cstride];
+            const float nx = fmaf(x, OCD_BUMP_IX, -cxj);
+            const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
             const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
             float val = 0.0f, vx = 0.0f, vy = 0.0f;
             if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
@@ -392,10 +402,10 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
 
 // Feature vector phi[K] at one world state, in the reference's order and op order.
 // SCALED: the other cars' coordinates come from a FAST slab (already divided by the half-width).
-template <int LT, bool PRECISE, bool SCALED>
+template <int LT, bool PRECISE, bool SCALED, bool LIN = false>
 __device__ __forceinline__ void feature_values(const KParams &k, float x, float y, float v, float sn,
                                                const float *oth, int jstride, int cstride,
-                                               float (&phi)[OCD_MAX_LANES + 4]) {
+                                               float (&phi)[OCD_MAX_LANES + 4], float tf = 0.0f) {
     const int L = LT > 0 ? LT : k.L;
     {
         const float e = __fsub_rn(__fmul_rn(v, sn), k.ts);
@@ -413,9 +423,11 @@ __device__ __forceinline__ void feature_values(const KParams &k, float x, float 
     float best = 0.0f;
     for (int j = 0; j < k.NO; ++j) {
         float iw, bx, dbx, by, dby;
-        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(x, oth[j * jstride], OCD_BUMP_HX, OCD_BUMP_IX, iw), bx, dbx);
-        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(y, oth[j * jstride + cstride], OCD_BUMP_HY, OCD_BUMP_IY, iw),
-                        by, dby);
+        const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
+        const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
+                              : oth[j * jstride + cstride];
+        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(x, cxj, OCD_BUMP_HX, OCD_BUMP_IX, iw), bx, dbx);
+        bump_n<PRECISE>(bump_offset<PRECISE, SCALED>(y, cyj, OCD_BUMP_HY, OCD_BUMP_IY, iw), by, dby);
         const float val = __fmul_rn(bx, by);
         best = (j == 0) ? val : fmaxf(best, val);
     }
@@ -432,11 +444,12 @@ __device__ __forceinline__ void feature_values(const KParams &k, float x, float 
 }
 
 // w . phi summed in feature order (linear_reward_car.py:53).  w[k] at w[k*ws].
-template <int LT, bool PRECISE, bool SCALED>
+template <int LT, bool PRECISE, bool SCALED, bool LIN = false>
 __device__ __forceinline__ float reward_value(const KParams &k, const float *w, int ws, float x, float y,
-                                              float v, float sn, const float *oth, int jstride, int cstride) {
+                                              float v, float sn, const float *oth, int jstride, int cstride,
+                                              float tf = 0.0f) {
     float phi[OCD_MAX_LANES + 4];
-    feature_values<LT, PRECISE, SCALED>(k, x, y, v, sn, oth, jstride, cstride, phi);
+    feature_values<LT, PRECISE, SCALED, LIN>(k, x, y, v, sn, oth, jstride, cstride, phi, tf);
     float r = 0.0f;
 #pragma unroll
     for (int i = 0; i < OCD_MAX_LANES + 4; ++i)
@@ -455,7 +468,25 @@ template <int HT>
 struct Traj {
     static constexpr int HM = HT > 0 ? HT : OCD_MAX_H;
     float ua[HM], uw[HM];                      // controls (acceleration, angular velocity)
+    __device__ __forceinline__ float acc(int t) const { return ua[t]; }
+    __device__ __forceinline__ float ang(int t) const { return uw[t]; }
 };
+
+// Controls of one thread kept in shared memory (used by the segmented solver for runtime / long
+// horizons, where 2H controls do not fit the register file).  Each thread owns 2H consecutive floats;
+// consecutive threads are an ODD number of floats apart, so a warp's accesses to the same (t, c) hit 32
+// different banks, while inside a segment every access is base + immediate.
+struct SmemTraj {
+    float *p;      // this thread's controls: (acc_t, ang_t) at p[2t], p[2t+1]
+    __device__ __forceinline__ float acc(int t) const { return p[2 * t]; }
+    __device__ __forceinline__ float ang(int t) const { return p[2 * t + 1]; }
+    __device__ __forceinline__ void set(int t, float a, float w) const {
+        p[2 * t] = a;
+        p[2 * t + 1] = w;
+    }
+};
+__host__ __device__ inline int seg_u_stride(int H) { return (2 * H) | 1; }
+__host__ __device__ inline int seg_ck_stride(int H, int SEG) { return (4 * ((H + SEG - 1) / SEG)) | 1; }
 
 template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE>
 __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
@@ -516,20 +547,22 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
 
 // R(u) = sum_t w . phi(s_{t+1}), value only, reference op order (naive_planner.py:43-77).
 // The slab is a FAST (scaled) one exactly when PRECISE is false.
-template <int HT, int LT, bool PRECISE>
+template <int HT, int LT, bool PRECISE, typename Controls, bool LIN = false>
 __device__ __forceinline__ float rollout_reward(const KParams &k, const float *wraw, int ws, float x0, float y0,
                                                 float v0, float th0, const float *oth, int P,
-                                                const Traj<HT> &u) {
+                                                const Controls &u) {
     const int H = HT > 0 ? HT : k.H;
     float x = x0, y = y0, v = v0, th = th0;
     float r = 0.0f;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
-        dynamics_step<PRECISE>(x, y, v, th, u.ua[t], u.uw[t], k.dt, k.dt2, k.mu);
+        dynamics_step<PRECISE>(x, y, v, th, u.acc(t), u.ang(t), k.dt, k.dt2, k.mu);
         float sn, cs;
         Mth<PRECISE>::sincos_(th, sn, cs);
-        r = __fadd_rn(r, reward_value<LT, PRECISE, !PRECISE>(k, wraw, ws, x, y, v, sn,
-                                                             oth + (size_t)t * k.NO * 2 * P, 2 * P, P));
+        r = __fadd_rn(r, LIN ? reward_value<LT, PRECISE, !PRECISE, LIN>(k, wraw, ws, x, y, v, sn, oth, 4 * P, P,
+                                                                         (float)(t + 1))
+                             : reward_value<LT, PRECISE, !PRECISE, false>(k, wraw, ws, x, y, v, sn,
+                                                                          oth + (size_t)t * k.NO * 2 * P, 2 * P, P));
     }
     return r;
 }
@@ -558,7 +591,120 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
         sgd_iteration<HT, NOT_, LT, PRECISE, true>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
-    return -rollout_reward<HT, LT, PRECISE>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+    return -rollout_reward<HT, LT, PRECISE, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Runtime / long horizons: the segmented adjoint.
+// The register file cannot hold 10 values per step for H = 15..64, and spilling them to local
+// memory is what makes a naive runtime-H kernel slow.  Instead the horizon is cut into segments of
+// SEG steps.  Pass 1 rolls the dynamics alone (no features) and checkpoints the state at every
+// segment start; pass 2 walks the segments backwards, re-running each segment forward from its
+// checkpoint WITH the feature gradients (register arrays of SEG entries) and then sweeping it in
+// reverse.  The expensive part -- the feature gradient -- is still evaluated exactly once per step,
+// so the cost over the register-resident kernel is one extra dynamics step (~15 %).  Controls
+// [H][2] and checkpoints [nseg][4] live in shared memory, thread index fastest.
+// ---------------------------------------------------------------------------------------------
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN>
+__device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW &w, float x0, float y0, float v0,
+                                                  float th0, const float *oth, int P, const SmemTraj &u, float *ck) {
+    const int H = k.H;
+    const int NO = NOT_ > 0 ? NOT_ : k.NO;
+    const int nseg = (H + SEG - 1) / SEG;
+    {   // pass 1: dynamics only, checkpoint every segment start (all segments but the last are full)
+        float x = x0, y = y0, v = v0, th = th0;
+        const float *us = u.p;
+        float *c = ck;
+#pragma unroll 1
+        for (int sg = 0; sg < nseg - 1; ++sg, us += 2 * SEG, c += 4) {
+            c[0] = x; c[1] = y; c[2] = v; c[3] = th;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                float sn, cs;
+                Mth<PRECISE>::sincos_(th, sn, cs);
+                const float ac = fmaxf(fminf(us[2 * i], 4.0f), -8.0f);
+                const float oc = fmaxf(fminf(us[2 * i + 1], 4.0f), -4.0f);
+                const float total = fmaf(-k.mu, v * v, ac);
+                const float dist = fmaf(total, k.hdt2, v * k.dt);
+                x = fmaf(cs, dist, x);
+                y = fmaf(sn, dist, y);
+                v = fmaf(total, k.dt, v);
+                th = fmaf(oc, k.dt, th);
+            }
+        }
+        c[0] = x; c[1] = y; c[2] = v; c[3] = th;
+    }
+    float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
+    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    const int ostep = LIN ? 0 : NO * 2 * P;                    // slab floats per horizon step
+    float *us = u.p + 2 * SEG * (nseg - 1);
+    const float *c = ck + 4 * (nseg - 1);
+    const float *os = oth + (size_t)SEG * (nseg - 1) * ostep;
+    float tbase = (float)(SEG * (nseg - 1));                   // steps before this segment
+    int rem = H - SEG * (nseg - 1);                            // steps in this segment (last one may be short)
+#pragma unroll 1
+    for (int sg = nseg - 1; sg >= 0; --sg, us -= 2 * SEG, c -= 4, os -= SEG * ostep, rem = SEG, tbase -= (float)SEG) {
+        float x = c[0], y = c[1], v = c[2], th = c[3];
+        float sn, cs;
+        Mth<PRECISE>::sincos_(th, sn, cs);
+        float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
+        const float *ot = os;
+#pragma unroll
+        for (int i = 0; i < SEG; ++i, ot += ostep) {
+            if (i < rem) {
+                ua[i] = us[2 * i];
+                uw[i] = us[2 * i + 1];
+                const float ac = fmaxf(fminf(ua[i], 4.0f), -8.0f);
+                const float oc = fmaxf(fminf(uw[i], 4.0f), -4.0f);
+                const float total = fmaf(-k.mu, v * v, ac);
+                const float dist = fmaf(total, k.hdt2, v * k.dt);
+                sv[i] = v; sc[i] = cs; ss[i] = sn; sd[i] = dist;
+                x = fmaf(cs, dist, x);
+                y = fmaf(sn, dist, y);
+                v = fmaf(total, k.dt, v);
+                th = fmaf(oc, k.dt, th);
+                Mth<PRECISE>::sincos_(th, sn, cs);
+                feature_grad<NOT_, LT, PRECISE, LIN>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P, gx[i], gy[i],
+                                                     gv[i], gth[i], tbase + (float)(i + 1));
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < SEG; ++ii) {
+            const int i = SEG - 1 - ii;
+            if (i < rem) {
+                const float mx = gx[i] + lx, my = gy[i] + ly, mv = gv[i] + lv, mth = gth[i] + lth;
+                const float ld = fmaf(sc[i], mx, ss[i] * my);
+                const float a = ua[i], om = uw[i];
+                const bool in_a = (a >= -8.0f) && (a <= 4.0f);
+                const bool in_w = fabsf(om) <= 4.0f;
+                lv = fmaf(fmaf(c1, sv[i], 1.0f), mv, fmaf(c2, sv[i], k.dt) * ld);
+                lth = fmaf(sd[i], fmaf(sc[i], my, -(ss[i] * mx)), mth);
+                lx = mx;
+                ly = my;
+                const float ga = in_a ? fmaf(k.hdt2, ld, k.dt * mv) : 0.0f;
+                const float gw = in_w ? k.dt * mth : 0.0f;
+                us[2 * i] = fmaf(k.lr, ga, a);                 // u <- u - lr * d(-R)/du
+                us[2 * i + 1] = fmaf(k.lr, gw, om);
+            }
+        }
+    }
+}
+
+// The complete segmented solve for one (problem, start): start controls, n_iter iterations, final loss.
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN>
+__device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &w, const float *wraw, int ws,
+                                                 float x0, float y0, float v0, float th0, const float *oth, int P,
+                                                 int s, float cur_speed, const SmemTraj &u, float *ck) {
+    {
+        const float a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(cur_speed, cur_speed)) : 0.0f;
+        const int m = s % 3;
+        const float w0 = (m == 0) ? 0.0f : ((m == 1) ? -k.turn : k.turn);
+        for (int t = 0; t < k.H; ++t) u.set(t, a0, w0);
+    }
+#pragma unroll 1
+    for (int it = 0; it < k.n_iter; ++it)
+        sgd_iteration_seg<SEG, NOT_, LT, PRECISE, LIN>(k, w, x0, y0, v0, th0, oth, P, u, ck);
+    return -rollout_reward<0, LT, PRECISE, SmemTraj, LIN>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 
 }  // namespace ocd

@@ -73,22 +73,42 @@ struct Smem {
     float *u0;      // [S][2][P]       first control of every start (episode only)
     float *world;   // [C][4][P]       live world state (episode only)
     float *wtrue;   // [K]             true weights (episode only)
+    float *useg;    // [S*P][2H | 1]     controls of every thread (segmented kernels only)
+    float *ckpt;    // [S*P][4 nseg | 1] segment-start states (segmented kernels only)
 };
 
-__host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode) {
-    size_t n = (size_t)H * NO * 2 * P + (size_t)K * P + (size_t)S * P;
-    if (episode) n += (size_t)S * 2 * P + (size_t)(NO + 1) * 4 * P + K;
+static constexpr int kSeg = 5;    // steps per segment of the runtime-horizon kernels (register budget of the H=5 kernel)
+
+// lin: the slab holds (x0, dx, y0, dy) per other car instead of a position per horizon step
+// (worth its two extra FFMA per car and step only once the per-step slab would crowd out resident blocks)
+__host__ __device__ inline bool slab_is_linear(bool seg, bool precise, int other_mode, int H, int NO) {
+    return seg && !precise && other_mode == 0 && H * NO >= 100;
+}
+
+__host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode, bool seg, bool lin) {
+    size_t n = (size_t)(lin ? 4 * NO : H * NO * 2) * P + (size_t)K * P + (size_t)S * P;
+    if (episode) n += (size_t)S * 2 * P + (size_t)(NO + 1) * 4 * P + ((K + 3) / 4) * 4;
+    if (seg) n += (size_t)S * P * (seg_u_stride(H) + seg_ck_stride(H, kSeg));
     return n;
 }
 
-__device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool episode) {
+__device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool episode, bool seg, bool lin) {
     Smem m;
     m.oth = base;
-    m.wraw = m.oth + (size_t)k.H * k.NO * 2 * P;
+    m.wraw = m.oth + (size_t)(lin ? 4 * k.NO : k.H * k.NO * 2) * P;
     m.loss = m.wraw + (size_t)k.K * P;
-    m.u0 = m.loss + (size_t)k.S * P;
-    m.world = episode ? m.u0 + (size_t)k.S * 2 * P : nullptr;
-    m.wtrue = episode ? m.world + (size_t)(k.NO + 1) * 4 * P : nullptr;
+    float *next = m.loss + (size_t)k.S * P;
+    m.u0 = m.world = m.wtrue = m.useg = m.ckpt = nullptr;
+    if (episode) {
+        m.u0 = next;
+        m.world = m.u0 + (size_t)k.S * 2 * P;
+        m.wtrue = m.world + (size_t)(k.NO + 1) * 4 * P;
+        next = m.wtrue + ((k.K + 3) / 4) * 4;
+    }
+    if (seg) {
+        m.useg = next;
+        m.ckpt = m.useg + (size_t)k.S * P * seg_u_stride(k.H);
+    }
     return m;
 }
 
@@ -97,7 +117,17 @@ __device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool
 // with element stride ocs, or null for the constant-velocity model.
 template <bool PRECISE>
 __device__ __forceinline__ void predict_other(const KParams &k, float x, float y, float v, float th,
-                                              const float *oc, long long ocs, float *oth_col, int j, int P) {
+                                              const float *oc, long long ocs, float *oth_col, int j, int P,
+                                              bool lin = false) {
+    if (lin) {      // constant velocity: position after n steps = start + n * (cos th * v * dt, sin th * v * dt)
+        float sn, cs;
+        Mth<PRECISE>::sincos_(th, sn, cs);
+        oth_col[(size_t)(j * 4 + 0) * P] = slab_x<PRECISE>(x);
+        oth_col[(size_t)(j * 4 + 1) * P] = slab_x<PRECISE>(__fmul_rn(__fmul_rn(cs, v), k.dt));
+        oth_col[(size_t)(j * 4 + 2) * P] = slab_y<PRECISE>(y);
+        oth_col[(size_t)(j * 4 + 3) * P] = slab_y<PRECISE>(__fmul_rn(__fmul_rn(sn, v), k.dt));
+        return;
+    }
     for (int t = 0; t < k.H; ++t) {
         float a = 0.0f, om = 0.0f;
         if (oc) {
@@ -114,10 +144,12 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // k_solve
 // ---------------------------------------------------------------------------------------------
 template <int HT, int NOT_, int LT, bool PRECISE>
-__global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
+__global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
-    const Smem m = carve(smem_raw, k, P, false);
+    constexpr bool SEGK = (HT == 0);     // runtime horizon: segmented adjoint, controls in shared memory
+    const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
+    const Smem m = carve(smem_raw, k, P, false, SEGK, lin);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
     const bool live = b_raw < a.B;
@@ -135,27 +167,38 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ K
                 ocs = a.Bo;
                 oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
             }
-            predict_other<PRECISE>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P);
+            predict_other<PRECISE>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P, lin);
         }
     }
     __syncthreads();
 
     const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
     const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
-    Traj<HT> u;
-    init_start<HT>(k, s, a.cur_speed ? a.cur_speed[b] : v0, u);
-    const float loss = solve_start<HT, NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+    const float speed = a.cur_speed ? a.cur_speed[b] : v0;
+    const int H = HT > 0 ? HT : k.H;
+    Traj<(HT > 0 ? HT : 1)> u;                       // register-resident controls (compile-time horizon)
+    const SmemTraj us{SEGK ? m.useg + (size_t)threadIdx.x * seg_u_stride(k.H) : nullptr};   // shared-memory controls
+    float loss;
+    if (SEGK) {
+        float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
+        loss = (!PRECISE && lin)
+                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p,
+                                                                         P, s, speed, us, ck)
+                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
+                                                                     s, speed, us, ck);
+    } else {
+        init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
+        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+    }
     m.loss[s * P + p] = loss;
     if (live) {
         a.losses[(size_t)s * B + b] = loss;
         if (a.all_plans) {
-            const int H = HT > 0 ? HT : k.H;
-#pragma unroll
-            for (int t = 0; t < Traj<HT>::HM; ++t)
-                if (t < H) {
-                    a.all_plans[((size_t)(s * H + t) * 2 + 0) * B + b] = u.ua[t];
-                    a.all_plans[((size_t)(s * H + t) * 2 + 1) * B + b] = u.uw[t];
-                }
+#pragma unroll(HT > 0 ? HT : 1)
+            for (int t = 0; t < H; ++t) {
+                a.all_plans[((size_t)(s * H + t) * 2 + 0) * B + b] = SEGK ? us.acc(t) : u.acc(SEGK ? 0 : t);
+                a.all_plans[((size_t)(s * H + t) * 2 + 1) * B + b] = SEGK ? us.ang(t) : u.ang(SEGK ? 0 : t);
+            }
         }
     }
     __syncthreads();
@@ -167,14 +210,12 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ K
         if (l < bl) { bl = l; bi = q; }
     }
     if (live && s == bi) {
-        const int H = HT > 0 ? HT : k.H;
         a.best[b] = bi;
-#pragma unroll
-        for (int t = 0; t < Traj<HT>::HM; ++t)
-            if (t < H) {
-                a.plan[(size_t)(t * 2 + 0) * B + b] = u.ua[t];
-                a.plan[(size_t)(t * 2 + 1) * B + b] = u.uw[t];
-            }
+#pragma unroll(HT > 0 ? HT : 1)
+        for (int t = 0; t < H; ++t) {
+            a.plan[(size_t)(t * 2 + 0) * B + b] = SEGK ? us.acc(t) : u.acc(SEGK ? 0 : t);
+            a.plan[(size_t)(t * 2 + 1) * B + b] = SEGK ? us.ang(t) : u.ang(SEGK ? 0 : t);
+        }
     }
 }
 
@@ -182,11 +223,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve(const __grid_constant__ K
 // k_episode
 // ---------------------------------------------------------------------------------------------
 template <int HT, int NOT_, int LT, bool PRECISE>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;
-    const Smem m = carve(smem_raw, k, P, true);
+    constexpr bool SEGK = (HT == 0);
+    const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
+    const Smem m = carve(smem_raw, k, P, true, SEGK, lin);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
     const bool live = b_raw < a.B;
@@ -231,6 +274,10 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
             for (int j = 0; j < k.NO; ++j) {
                 const float *w = m.world + (size_t)(j + 1) * 4 * P + p;
                 float x = w[0], y = w[P], v = w[2 * P], th = w[3 * P];
+                if (lin) {
+                    predict_other<PRECISE>(k, x, y, v, th, nullptr, 0, m.oth + p, j, P, true);
+                    continue;
+                }
                 for (int t = 0; t < k.H; ++t) {
                     float oa = 0.0f, oo = 0.0f;
                     if (k.other_mode == 1 && sc.kind[j] == 1) {   // plan replayed from index 0 (quirk Q4)
@@ -247,12 +294,24 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
         __syncthreads();
 
         const float x0 = m.world[p], y0 = m.world[P + p], v0 = m.world[2 * P + p], th0 = m.world[3 * P + p];
-        Traj<HT> u;
-        init_start<HT>(k, s, v0, u);
-        const float loss = solve_start<HT, NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+        Traj<(HT > 0 ? HT : 1)> u;
+        const SmemTraj us{SEGK ? m.useg + (size_t)threadIdx.x * seg_u_stride(k.H) : nullptr};
+        float loss;
+        if (SEGK) {
+            float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
+            loss = (!PRECISE && lin)
+                       ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                             m.oth + p, P, s, v0, us, ck)
+                       : solve_start_seg<kSeg, NOT_, LT, PRECISE, false>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                         m.oth + p, P, s, v0, us, ck);
+        } else {
+            init_start<(HT > 0 ? HT : 1)>(k, s, v0, u);
+            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p,
+                                                                      P, u);
+        }
         m.loss[s * P + p] = loss;
-        m.u0[(s * 2 + 0) * P + p] = u.ua[0];
-        m.u0[(s * 2 + 1) * P + p] = u.uw[0];
+        m.u0[(s * 2 + 0) * P + p] = SEGK ? us.acc(0) : u.acc(0);
+        m.u0[(s * 2 + 1) * P + p] = SEGK ? us.ang(0) : u.ang(0);
         __syncthreads();
 
         if (s == 0) {
@@ -309,7 +368,8 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
-    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false) * sizeof(float);
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
+                                     slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
@@ -320,7 +380,8 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs &a, cudaStream_t st) {
-    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true) * sizeof(float);
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true, HT == 0,
+                                     slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
