@@ -246,3 +246,41 @@ def test_run_mpc_ord_cli_vis(capsys):
     # true weights on 3 inits, then the tuned weights of run_mpc_ord.py:34-35
     assert all(np.isfinite(h[1]) for h in m.history)
     assert "return of the tuned weights" in capsys.readouterr().out
+
+
+# ---- "next" rows: reward heat-map and generalisation evaluation -------------------------------------
+def test_reward_heatmap_matches_oracle_features():
+    import oracle as O
+    from l4dc_mpc_ocd_b200.heatmap import reward_heatmap
+    car, world, inits = finite_horizon_env(env_seeds=[1000000])
+    world.reset()
+    lo, hi = (-0.15, -1.4), (0.15, -0.4)
+    img = reward_heatmap(car, lo, hi, size=(24, 16))
+    assert img.shape == (16, 24)
+    xs = np.linspace(lo[0] + 1e-6, hi[0] - 1e-6, 24)
+    ys = np.linspace(lo[1] + 1e-6, hi[1] - 1e-6, 16)
+    p = O.OracleParams()
+    for (j, i) in ((0, 0), (5, 11), (9, 12), (15, 23), (10, 2)):
+        st = np.stack([c.state for c in world.cars]).astype(np.float32)
+        st[0, 0], st[0, 1] = xs[i], ys[j]
+        ref = float(np.dot(car.weights, O.features(p, st)))
+        assert abs(img[j, i] - ref) <= 2e-6 * max(1.0, abs(ref))
+    # the collision bump of the other car (at x=0, y=-0.6) must show up as the minimum of the map
+    j, i = np.unravel_index(np.argmin(img[:, 8:16]), img[:, 8:16].shape)
+    assert abs(ys[j] - (-0.6)) < 0.1
+
+
+def test_generalization_evaluation_is_one_launch():
+    from l4dc_mpc_ocd_b200.experiments import generalization_data as gd
+    env = run_mpc_ord.envs["local_opt"]
+    weights = {(1, 2): env["tuned_weights"], (3, 2): np.array([-5, 0., 0., -10, 0, -50, -50])}
+    res = gd.evaluate_on_test_inits("local_opt", weights, n_test=4)
+    assert sorted(res) == [0, 1, 2, 3] and set(res[0]) == set(weights)
+    # one of them, the serial way
+    car, world, test_inits = gd.make_test_env("local_opt", 4)
+    m = MPC_ORD(world, car, [], env["eval_horizon"], num_samples=env["num_eval_samples"], verbose=False)
+    one = m.eval_weights_for_init(test_inits[2], np.asarray(weights[(1, 2)], np.float64), False)
+    assert abs(one - res[2][(1, 2)]) <= 1e-6 * abs(one)
+    hist = [(np.ones(7), -3.0), (np.arange(7.0), -1.0), (np.zeros(7), -2.0)]
+    np.testing.assert_array_equal(gd.best_weights(hist), np.arange(7.0))
+    np.testing.assert_array_equal(gd.best_weights(hist, num_evals=1), np.ones(7))
