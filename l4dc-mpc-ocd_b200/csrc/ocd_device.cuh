@@ -287,8 +287,10 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
             near = fminf(near, fabsf(x - k.lane_mid[i - 1]));
         }
     const bool close = near < 1e-6f;
-    if (__any_sync(OCD_FULL, close))
-        if (close) dsel = lane_min_offset_exact<LT>(k, x);
+    if (__any_sync(OCD_FULL, close)) {        // whole warp takes the exact rule: no divergence to reconverge
+        const float exact = lane_min_offset_exact<LT>(k, x);
+        dsel = close ? exact : dsel;
+    }
     return dsel;
 }
 
