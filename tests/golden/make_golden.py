@@ -341,7 +341,7 @@ SIMPLE = {"primitives": part_primitives, "features": part_features, "mpc_reward"
           "plans": part_plans, "planner_kats": part_planner_kats}
 
 
-def run_part(part: str):
+def run_part(part: str, outdir: Path = HERE):
     _setup_reference_imports()
     t0 = time.time()
     if part in SIMPLE:
@@ -352,7 +352,7 @@ def run_part(part: str):
     data["generated_by"] = "tests/golden/make_golden.py --part " + part
     data["generator_seconds"] = round(time.time() - t0, 1)
     fname = part.replace(":", "_") + ".json"
-    with open(HERE / fname, "w") as f:
+    with open(Path(outdir) / fname, "w") as f:
         json.dump(data, f, indent=1)
     print("wrote", fname, "in %.0fs" % (time.time() - t0), flush=True)
 
@@ -362,10 +362,11 @@ def main():
     ap.add_argument("--part")
     ap.add_argument("--all", action="store_true")
     ap.add_argument("--jobs", type=int, default=8)
+    ap.add_argument("--outdir", default=str(HERE), help="where to write the JSON (default: tests/golden)")
     args = ap.parse_args()
     parts = list(SIMPLE) + ["episode:%s:%s:%s" % e for e in EPISODES]
     if args.part:
-        run_part(args.part)
+        run_part(args.part, Path(args.outdir).resolve())
         return
     if not args.all:
         ap.error("--part NAME or --all")
