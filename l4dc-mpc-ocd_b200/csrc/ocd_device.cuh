@@ -343,37 +343,89 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         // exactly 0 and takes every derivative with it, so no branch and no select is needed.
         // hx, hy below are d(val)/d(position) without the constant -2/half-width (folded into
         // wcx, wcy).  A warp with every lane outside every support skips the transcendental part.
-        float best = 0.0f, hx = 0.0f, hy = 0.0f, cnt = 1.0f;
-        // runtime car count: fully unrolled with uniform guards, so that every slab address is an
-        // immediate and no loop counter is carried
+        float hx = 0.0f, hy = 0.0f;
+        if (NOT_ > 0) {
+            // compile-time car count (the shipped scenarios): value and derivatives per car, TF's even
+            // split among exact ties applied on the fly (the replanning scenario's two other cars start
+            // on top of each other, so exact ties are the normal case there)
+            float best = 0.0f, cnt = 1.0f;
 #pragma unroll
-        for (int j = 0; j < (NOT_ > 0 ? NOT_ : OCD_MAX_OTHER); ++j) {
-            if (NOT_ == 0 && j >= NO) break;
-            const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
-            const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
-                                  : oth[j * jstride + cstride];
-            const float nx = fmaf(x, OCD_BUMP_IX, -cxj);
-            const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
-            const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
-            float val = 0.0f, vx = 0.0f, vy = 0.0f;
-            if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
-                const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
-                val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
-                vx = (val * nx) * (rx * rx);
-                vy = (val * ny) * (ry * ry);
+            for (int j = 0; j < NOT_; ++j) {
+                const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
+                const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
+                                      : oth[j * jstride + cstride];
+                const float nx = fmaf(x, OCD_BUMP_IX, -cxj);
+                const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
+                const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
+                float val = 0.0f, vx = 0.0f, vy = 0.0f;
+                if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
+                    const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
+                    val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
+                    vx = (val * nx) * (rx * rx);
+                    vy = (val * ny) * (ry * ry);
+                }
+                if (NOT_ == 1) {
+                    hx = vx; hy = vy;
+                } else if (j == 0 || val > best) {
+                    best = val; hx = vx; hy = vy; cnt = 1.0f;
+                } else if (val == best) {
+                    hx += vx; hy += vy; cnt += 1.0f;
+                }
             }
-            if (NOT_ == 1) {
-                hx = vx; hy = vy;
-            } else if (j == 0 || val > best) {
-                best = val; hx = vx; hy = vy; cnt = 1.0f;
-            } else if (val == best) {
-                hx += vx; hy += vy; cnt += 1.0f;
+            if (NOT_ != 1 && cnt != 1.0f) {
+                const float r = __fdiv_rn(1.0f, cnt);
+                hx *= r;
+                hy *= r;
             }
-        }
-        if (NOT_ != 1 && cnt != 1.0f) {
-            const float r = __fdiv_rn(1.0f, cnt);
-            hx *= r;
-            hy *= r;
+        } else {
+            // runtime car count (sweeps with many cars): only the VALUE is computed per car; the winner's
+            // offsets and reciprocals ride along through selects and its derivatives are formed once, after
+            // the loop.  Fully unrolled with uniform guards, so every slab address is an immediate.  An exact
+            // tie between two non-zero values (measure zero, but TF splits the gradient there) is flagged and
+            // sends the warp through the exact rule.
+            float best = 0.0f, bnx = 0.0f, bny = 0.0f, brx = 0.0f, bry = 0.0f;
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < OCD_MAX_OTHER; ++j) {
+                if (j >= NO) break;
+                const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
+                const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
+                                      : oth[j * jstride + cstride];
+                const float nx = fmaf(x, OCD_BUMP_IX, -cxj);
+                const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
+                const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
+                if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
+                    const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
+                    const float val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
+                    tie = tie || (val == best && val > 0.0f);
+                    const bool gt = val > best;
+                    best = fmaxf(best, val);
+                    bnx = gt ? nx : bnx; bny = gt ? ny : bny; brx = gt ? rx : brx; bry = gt ? ry : bry;
+                }
+            }
+            hx = (best * bnx) * (brx * brx);
+            hy = (best * bny) * (bry * bry);
+            if (__any_sync(OCD_FULL, tie)) {
+                float b2 = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
+                for (int j = 0; j < NO; ++j) {
+                    const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
+                    const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
+                                          : oth[j * jstride + cstride];
+                    const float nx = fmaf(x, OCD_BUMP_IX, -cxj), ny = fmaf(y, OCD_BUMP_IY, -cyj);
+                    const float rx = Mth<false>::rcp_(fmaxf(fmaf(-nx, nx, 1.0f), 1e-6f));
+                    const float ry = Mth<false>::rcp_(fmaxf(fmaf(-ny, ny, 1.0f), 1e-6f));
+                    const float val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
+                    const float vx = (val * nx) * (rx * rx), vy = (val * ny) * (ry * ry);
+                    if (j == 0 || val > b2) {
+                        b2 = val; sx = vx; sy = vy; cnt = 1.0f;
+                    } else if (val == b2) {
+                        sx += vx; sy += vy; cnt += 1.0f;
+                    }
+                }
+                const float r = __fdiv_rn(1.0f, cnt);
+                hx = tie ? sx * r : hx;
+                hy = tie ? sy * r : hy;
+            }
         }
         gx = fmaf(w.wcx, hx, gx);
         gy = w.wcy * hy;

@@ -369,3 +369,69 @@ def test_full_size_properties(engine):
     same = ref["best"] == a["best"].cpu().numpy()[sel]
     assert same.mean() > 0.9
     assert np.max(np.abs(got[same] - ref["plan"][same])) <= 1e-3
+
+
+# ---- edge shapes: limits of the ABI, ragged batches, every weight / control sharing mode -----------------
+@pytest.mark.parametrize("H,C,lane_x,extra,other_mode,B", [
+    (1, 2, (-0.1, 0.0, 0.1), False, 0, 33),            # shortest horizon, batch not a multiple of the block
+    (64, 2, (-0.1, 0.0, 0.1), False, 0, 5),            # OCD_MAX_H
+    (5, 8, (-0.1, 0.0, 0.1), False, 0, 70),            # OCD_MAX_OTHER + 1 cars
+    (7, 3, (0.0,), False, 1, 31),                      # one lane
+    (4, 2, (-0.15, -0.05, 0.05, 0.15), True, 0, 64),   # OCD_MAX_LANES, six starts
+    (12, 4, (-0.05, 0.05), True, 1, 40),               # segmented kernel with six starts and known controls
+    (5, 3, (-0.05, 0.05), False, 1, 1),                # a single problem
+])
+def test_edge_shapes_vs_oracle(engine, H, C, lane_x, extra, other_mode, B):
+    rng = np.random.default_rng(H * 100 + C)
+    batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=H + C)
+    oc = 0.2 * synthetic.make_other_controls(B, C, H) if other_mode else None
+    lr = 0.1 if H <= 8 else 0.02 * 5 / H        # long horizons need a much smaller step to stay stable
+    op = O.OracleParams(H=H, C=C, lane_x=lane_x, n_iter=12, num_lanes=len(lane_x), other_mode=other_mode,
+                        extra_inits=extra, lr=lr)
+    w_full = batch["weights"][batch["weight_idx"]]
+    ref = O.generate_plan_batch(op, batch["world"], w_full, other_controls=oc)
+    ref64 = O.generate_plan_batch(op, batch["world"].astype(np.float64), w_full.astype(np.float64),
+                                  other_controls=None if oc is None else oc.astype(np.float64), dtype=np.float64)
+    # what float32 itself loses on these problems (long horizons with random weights reach large rewards)
+    ok64 = np.isfinite(ref["losses"]) & np.isfinite(ref64["losses"])
+    slack_l = 3.0 * _rel(ref["losses"][ok64], ref64["losses"][ok64], floor=1.0)
+    slack_u = 3.0 * float(np.nanmax(np.abs(ref["plan"] - ref64["plan"])))
+    for mode in (ocd.MATH_FAST, ocd.MATH_PRECISE):
+        p = _pp(op, mode)
+        res = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"], other_controls=oc,
+                           all_plans=True)
+        res = {k: v.cpu().numpy() for k, v in res.items()}
+        assert res["plan"].shape == (B, H, 2) and res["losses"].shape == (B, p.S) and res["all_plans"].shape == (B, p.S, H, 2)
+        # 12 iterations from fixed starts: well conditioned, so every problem and every start must agree
+        tol = 2e-4 if mode == ocd.MATH_FAST else 2e-5
+        # a diverging start (H=64 with lr tuned for H=5) is NaN in the reference too: same NaN pattern required
+        assert np.array_equal(np.isnan(res["losses"]), np.isnan(ref["losses"]))
+        fin = np.isfinite(ref["losses"])
+        assert _rel(res["losses"][fin], ref["losses"][fin], floor=1.0) <= tol + slack_l
+        same = (res["best"] == ref["best"]) & np.isfinite(ref["plan"]).all(axis=(1, 2))
+        assert same.mean() >= 0.75
+        assert np.max(np.abs(res["plan"][same] - ref["plan"][same])) <= tol + slack_u
+        np.testing.assert_array_equal(res["plan"], res["all_plans"][np.arange(B), res["best"]])
+    # weight sharing modes give identical results: one vector for all, one per problem, indexed
+    p = _pp(op, ocd.MATH_FAST)
+    one_w = batch["weights"][0]
+    a = engine.solve(p, batch["world"], one_w, other_controls=oc)
+    b = engine.solve(p, batch["world"], np.tile(one_w, (B, 1)), other_controls=oc)
+    c = engine.solve(p, batch["world"], batch["weights"], weight_idx=np.zeros(B, np.int32), other_controls=oc)
+    for k in ("plan", "losses", "best"):
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k])
+    if other_mode:      # one control sequence shared by every problem == the same sequence repeated
+        d = engine.solve(p, batch["world"], one_w, other_controls=oc[:1])
+        e = engine.solve(p, batch["world"], one_w, other_controls=np.repeat(oc[:1], B, axis=0))
+        assert torch.equal(d["plan"], e["plan"])
+
+
+def test_nan_loss_follows_python_min(engine):
+    """losses.index(min(losses)) (naive_planner.py:161-164): a NaN loss in slot 0 wins, later NaNs never do."""
+    p = ocd.PlannerParams(n_iter=3)
+    world = np.array([[[0.0, -0.9, 0.8, np.pi / 2], [0.0, -0.6, 0.5, np.pi / 2]],
+                      [[np.nan, -0.9, 0.8, np.pi / 2], [0.0, -0.6, 0.5, np.pi / 2]]], np.float32)
+    res = engine.solve(p, world, np.array([-1, 0, 0, 0, -1, -5, -5], np.float32))
+    losses, best = res["losses"].cpu().numpy(), res["best"].cpu().numpy()
+    assert np.isfinite(losses[0]).all() and best[0] == int(np.argmin(losses[0]))
+    assert np.isnan(losses[1]).all() and best[1] == 0
