@@ -435,3 +435,25 @@ def test_nan_loss_follows_python_min(engine):
     losses, best = res["losses"].cpu().numpy(), res["best"].cpu().numpy()
     assert np.isfinite(losses[0]).all() and best[0] == int(np.argmin(losses[0]))
     assert np.isnan(losses[1]).all() and best[1] == 0
+
+
+def test_torch_custom_ops_match_engine(engine):
+    from l4dc_mpc_ocd_b200 import torch_ops as T
+    B = 200
+    batch = synthetic.make_batch(B, seed=21)
+    p = ocd.PlannerParams()
+    dev = engine.device
+    world = torch.as_tensor(batch["world"], device=dev).permute(1, 2, 0).contiguous()
+    w = torch.as_tensor(batch["weights"], device=dev).t().contiguous()
+    idx = torch.as_tensor(batch["weight_idx"], device=dev)
+    plan, losses, best = torch.ops.ocd_b200.solve(world, w, idx, None, T.pack_params(p))
+    ref = engine.solve_soa(p, world, w, w.shape[1], idx)
+    assert torch.equal(plan, ref["plan"]) and torch.equal(losses, ref["losses"]) and torch.equal(best, ref["best"])
+    spec = O.scenario_params("replanning")
+    pp, sc = _pp(spec.params, ocd.MATH_FAST), _sc(spec.scenario)
+    wt = torch.as_tensor(spec.designer_weights / np.linalg.norm(spec.designer_weights), dtype=torch.float32, device=dev)
+    ri = torch.as_tensor(np.tile(spec.example_init, (6, 1)).T.copy(), dtype=torch.float32, device=dev)
+    ul = torch.as_tensor([1, 2, 1, 2, 1, 2], dtype=torch.int32, device=dev)
+    ret = torch.ops.ocd_b200.episodes(ri, wt[:, None].contiguous(), None, wt, ul, T.pack_params(pp), T.pack_scenario(sc), 6)
+    ref2 = engine.episodes_soa(pp, sc, ri, wt[:, None].contiguous(), 1, wt, 6, unlucky_idx=ul)["returns"]
+    assert torch.equal(ret, ref2)

@@ -191,3 +191,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
     assert "workload" in line["config"]
+
+
+def test_torch_custom_ops_register_and_refuse_cpu():
+    import torch
+    from l4dc_mpc_ocd_b200 import torch_ops as T
+    p = ocd.PlannerParams(H=6, C=3, lane_x=(-0.05, 0.05), extra_inits=True)
+    assert T.unpack_params(T.pack_params(p)) == p
+    sc = ocd.Scenario(init_state=[[0, -0.7, 0.8, 1.57]] * 2, kind=[1, 0], friction=[0.2, 0.0],
+                      control=[[0, 0], [0.1, 0.2]], plan=[[[0, 0], [0.7, 2.7]], []], critical_t=4)
+    back = T.unpack_scenario(T.pack_scenario(sc))
+    assert back.kind == [1, 0] and back.plan[0][1] == [0.7, 2.7] and back.plan[1] == [] and back.critical_t == 4
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():          # shape inference needs no device
+        out = torch.ops.ocd_b200.solve(torch.empty((3, 4, 100)), torch.empty((6, 1)), None, None, T.pack_params(p))
+        assert [tuple(o.shape) for o in out] == [(6, 2, 100), (6, 100), (100,)]
+    with pytest.raises(RuntimeError):    # no CPU kernel behind the op
+        torch.ops.ocd_b200.solve(torch.zeros((3, 4, 2)), torch.zeros((6, 1)), None, None, T.pack_params(p))
