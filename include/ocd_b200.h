@@ -32,12 +32,13 @@
 extern "C" {
 #endif
 
-#define OCD_ABI_VERSION 1
+#define OCD_ABI_VERSION 2
 #define OCD_MAX_LANES   4
 #define OCD_MAX_OTHER   7     /* other cars per world (C <= 8)            */
 #define OCD_MAX_PLAN    16    /* FixedPlanCar plan length                 */
 #define OCD_MAX_H       64    /* planning horizon                         */
 #define OCD_MAX_STARTS  6
+#define OCD_LBFGS_MAX_H 16    /* horizon limit of the opt-in L-BFGS optimiser     */
 
 enum {
     OCD_OK       = 0,
@@ -60,6 +61,9 @@ typedef struct {
     int32_t other_mode;   /* 0: other cars keep velocity; 1: known controls (naive_planner.py:53-66)*/
     int32_t extra_inits;  /* 3 more starts with a0 = friction*v^2 (naive_planner.py:112-116)        */
     int32_t math_mode;    /* 0: MUFU intrinsics (sin/cos/ex2/rcp.approx); 1: IEEE div + libdevice   */
+    int32_t optimizer;    /* 0: the reference's fixed-budget SGD (naive_planner.py:151-153);
+                           * 1: L-BFGS, at most n_iter iterations per start (opt-in; see ocd_solve_batch) */
+    int32_t reserved;     /* must be 0                                                              */
     /* Python floats in the reference; kept as doubles and cast to float32 at the point of
      * use exactly as TensorFlow does (e.g. dt**2 is squared in double, then cast).            */
     double  lr;           /* learning_rate (naive_planner.py:20,28)                                 */
@@ -127,6 +131,10 @@ int ocd_reward_grad_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
 /* NaivePlanner.generate_plan (interact_drive/planner/naive_planner.py:81-164) + Keras SGD
  * (call sites :28,:153): S starts x n_iter gradient steps, final loss per start, first-minimum
  * argmin.  cur_speed ([B] or NULL -> world's robot speed) feeds the extra_inits starts (:114-116).
+ * With params.optimizer == 1 each start is minimised by L-BFGS instead (two-loop recursion with 4
+ * correction pairs, Armijo backtracking, first step of length lr; H <= OCD_LBFGS_MAX_H; precise math).
+ * That stands in for the reference's never-enabled `use_lbfgs` branch (naive_planner.py:127-149, TFP's
+ * lbfgs_minimize): same role, its own semantics -- there is nothing in the reference to pin it to.
  * Outputs: plan [H][2][B] (the selected start), losses [S][B], best [B];
  * all_plans [S][H][2][B] optional. */
 int ocd_solve_batch(const ocd_params *p, const float *world /*[C][4][B]*/,

@@ -6,10 +6,11 @@
 """
 from . import _native  # noqa: F401  (raises ImportError when libocd_b200.so has not been built)
 from .engine import (  # noqa: F401
-    Engine, HostContext, PlannerParams, Scenario, MATH_FAST, MATH_PRECISE, device_count,
+    Engine, HostContext, PlannerParams, Scenario, MATH_FAST, MATH_PRECISE, OPT_SGD, OPT_LBFGS, device_count,
 )
 
-__all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "device_count"]
+__all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "OPT_SGD", "OPT_LBFGS",
+           "device_count"]
 
 
 def install_as_reference() -> None:

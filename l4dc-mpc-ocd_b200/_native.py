@@ -12,8 +12,9 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libocd_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LANES, MAX_OTHER, MAX_PLAN, MAX_H, MAX_STARTS = 4, 7, 16, 64, 6
+LBFGS_MAX_H = 16
 OK, EINVAL, EUNSUP, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 SMOOTH_F, SMOOTH_THRESHOLD, SMOOTH_BUMP = 0, 1, 2
 
@@ -31,7 +32,7 @@ class ocd_params(C.Structure):
     _fields_ = [
         ("H", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("n_iter", C.c_int32),
         ("num_lanes", C.c_int32), ("other_mode", C.c_int32), ("extra_inits", C.c_int32),
-        ("math_mode", C.c_int32),
+        ("math_mode", C.c_int32), ("optimizer", C.c_int32), ("reserved", C.c_int32),
         ("lr", C.c_double), ("dt", C.c_double), ("friction", C.c_double), ("target_speed", C.c_double),
         ("lane_x", C.c_double * MAX_LANES),
     ]

@@ -106,6 +106,170 @@ k_dynamics(const float *state, const float *control, float dt, float dt2, float 
     next[b] = x; next[B + b] = y; next[2 * B + b] = v; next[3 * B + b] = th;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_solve_lbfgs -- the opt-in L-BFGS optimiser (params.optimizer == 1; include/ocd_b200.h).
+// Same block shape, slab and argmin as k_solve; per (problem, start) the thread runs L-BFGS on
+// f(u) = -R(u): two-loop recursion over 4 correction pairs held in local memory, Armijo backtracking,
+// gradient from the same closed-form adjoint.  Lanes of a warp take different numbers of line-search
+// trials, so the warp-voting FAST feature code cannot be used here: the kernel always runs the precise
+// math path.  The CPU restatement used by the parity tests mirrors this loop statement for statement.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kLbfgsM = 4, kLbfgsLS = 6, kLbfgsN = 2 * OCD_LBFGS_MAX_H;
+
+__device__ __forceinline__ float lbfgs_value_grad(const KParams &k, const GradW &gw, const float *wraw, int ws, float x0,
+                                                  float y0, float v0, float th0, const float *oth, int P,
+                                                  const float *uf, float *g /* null: value only */) {
+    Traj<0> u;
+    for (int t = 0; t < k.H; ++t) {
+        u.ua[t] = uf[2 * t];
+        u.uw[t] = uf[2 * t + 1];
+    }
+    const float f = -rollout_reward<0, 0, true>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+    if (g) {
+        float ga[OCD_MAX_H], go[OCD_MAX_H], sn0, cs0;
+        Mth<true>::sincos_(th0, sn0, cs0);
+        sgd_iteration<0, 0, 0, true, false>(k, gw, x0, y0, v0, th0, sn0, cs0, oth, P, u, ga, go);
+        for (int t = 0; t < k.H; ++t) {            // gradient of f = -R
+            g[2 * t] = -ga[t];
+            g[2 * t + 1] = -go[t];
+        }
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(kMaxThreads) k_solve_lbfgs(const __grid_constant__ KParams k, const SolveArgs a) {
+    extern __shared__ float smem_raw[];
+    constexpr int P = kP;
+    const Smem m = carve(smem_raw, k, P, false, false, false);
+    const int p = threadIdx.x % P, s = threadIdx.x / P;
+    const long long b_raw = (long long)blockIdx.x * P + p;
+    const bool live = b_raw < a.B;
+    const long long b = live ? b_raw : a.B - 1;
+    const long long B = a.B;
+    if (s == 0) {
+        const long long wc = weight_column(a.weight_idx, a.Bw, b);
+        for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.weights[(size_t)i * a.Bw + wc];
+        for (int j = 0; j < k.NO; ++j) {
+            const float *st = a.world + (size_t)(j + 1) * 4 * B + b;
+            const float *oc = nullptr;
+            long long ocs = 0;
+            if (k.other_mode == 1) {
+                ocs = a.Bo;
+                oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
+            }
+            predict_other<true>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P);
+        }
+    }
+    __syncthreads();
+    const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
+    const GradW gw = make_gradw<0>(k, m.wraw + p, P);
+    const float *wraw = m.wraw + p, *oth = m.oth + p;
+    const int n = 2 * k.H;
+    float u[kLbfgsN], g[kLbfgsN], gt[kLbfgsN], d[kLbfgsN], ut[kLbfgsN], q[kLbfgsN];
+    float Sh[kLbfgsM][kLbfgsN], Yh[kLbfgsM][kLbfgsN], rho[kLbfgsM], al[kLbfgsM];
+    {
+        const float speed = a.cur_speed ? a.cur_speed[b] : v0;
+        const float a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(speed, speed)) : 0.0f;
+        const int mm = s % 3;
+        const float w0 = (mm == 0) ? 0.0f : ((mm == 1) ? -k.turn : k.turn);
+        for (int t = 0; t < k.H; ++t) {
+            u[2 * t] = a0;
+            u[2 * t + 1] = w0;
+        }
+    }
+    float f = lbfgs_value_grad(k, gw, wraw, P, x0, y0, v0, th0, oth, P, u, g);
+    float sy_last = 0.0f, yy_last = 1.0f;
+    int kk = 0, head = 0;
+    for (int it = 0; it < k.n_iter; ++it) {
+        for (int j = 0; j < n; ++j) q[j] = g[j];
+        for (int i = 0; i < kk; ++i) {                      // newest pair first
+            const int idx = (head - 1 - i + 2 * kLbfgsM) % kLbfgsM;
+            float dot = 0.0f;
+            for (int j = 0; j < n; ++j) dot = __fadd_rn(dot, __fmul_rn(Sh[idx][j], q[j]));
+            al[i] = __fmul_rn(rho[idx], dot);
+            for (int j = 0; j < n; ++j) q[j] = __fsub_rn(q[j], __fmul_rn(al[i], Yh[idx][j]));
+        }
+        {
+            const float gamma = (kk > 0) ? __fdiv_rn(sy_last, yy_last) : k.lr;
+            for (int j = 0; j < n; ++j) q[j] = __fmul_rn(gamma, q[j]);
+        }
+        for (int i = kk - 1; i >= 0; --i) {                 // oldest pair first
+            const int idx = (head - 1 - i + 2 * kLbfgsM) % kLbfgsM;
+            float dot = 0.0f;
+            for (int j = 0; j < n; ++j) dot = __fadd_rn(dot, __fmul_rn(Yh[idx][j], q[j]));
+            const float bb = __fmul_rn(rho[idx], dot);
+            for (int j = 0; j < n; ++j) q[j] = __fadd_rn(q[j], __fmul_rn(Sh[idx][j], __fsub_rn(al[i], bb)));
+        }
+        float gd = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            d[j] = -q[j];
+            gd = __fadd_rn(gd, __fmul_rn(g[j], d[j]));
+        }
+        if (!(gd < 0.0f)) {                                 // not a descent direction: restart
+            kk = 0;
+            gd = 0.0f;
+            for (int j = 0; j < n; ++j) {
+                d[j] = __fmul_rn(-k.lr, g[j]);
+                gd = __fadd_rn(gd, __fmul_rn(g[j], d[j]));
+            }
+        }
+        if (!(gd < 0.0f)) break;
+        float t = 1.0f, ft = f;
+        bool ok = false;
+        for (int ls = 0; ls < kLbfgsLS; ++ls) {
+            for (int j = 0; j < n; ++j) ut[j] = __fadd_rn(u[j], __fmul_rn(t, d[j]));
+            ft = lbfgs_value_grad(k, gw, wraw, P, x0, y0, v0, th0, oth, P, ut, nullptr);
+            if (ft <= __fadd_rn(f, __fmul_rn(__fmul_rn(1e-4f, t), gd))) {
+                ok = true;
+                break;
+            }
+            t = __fmul_rn(t, 0.5f);
+        }
+        if (!ok) break;
+        lbfgs_value_grad(k, gw, wraw, P, x0, y0, v0, th0, oth, P, ut, gt);
+        {
+            float sy = 0.0f, yy = 0.0f;
+            for (int j = 0; j < n; ++j) {
+                const float sj = __fsub_rn(ut[j], u[j]), yj = __fsub_rn(gt[j], g[j]);
+                Sh[head][j] = sj;
+                Yh[head][j] = yj;
+                sy = __fadd_rn(sy, __fmul_rn(sj, yj));
+                yy = __fadd_rn(yy, __fmul_rn(yj, yj));
+            }
+            if (yy > 0.0f && sy > __fmul_rn(1e-10f, yy)) {
+                rho[head] = __fdiv_rn(1.0f, sy);
+                head = (head + 1) % kLbfgsM;
+                if (kk < kLbfgsM) ++kk;
+                sy_last = sy;
+                yy_last = yy;
+            }
+        }
+        for (int j = 0; j < n; ++j) {
+            u[j] = ut[j];
+            g[j] = gt[j];
+        }
+        f = ft;
+    }
+    const float loss = lbfgs_value_grad(k, gw, wraw, P, x0, y0, v0, th0, oth, P, u, nullptr);
+    m.loss[s * P + p] = loss;
+    if (live) {
+        a.losses[(size_t)s * B + b] = loss;
+        if (a.all_plans)
+            for (int j = 0; j < n; ++j) a.all_plans[((size_t)s * n + j) * B + b] = u[j];
+    }
+    __syncthreads();
+    int bi = 0;
+    float bl = m.loss[p];
+    for (int qs = 1; qs < k.S; ++qs) {
+        const float l = m.loss[qs * P + p];
+        if (l < bl) { bl = l; bi = qs; }
+    }
+    if (live && s == bi) {
+        a.best[b] = bi;
+        for (int j = 0; j < n; ++j) a.plan[(size_t)j * B + b] = u[j];
+    }
+}
+
 // math_utils.py helpers as operators (precise math, reference op order)
 __global__ void __launch_bounds__(256)
 k_smooth(int kind, const float *z, float a, float b, float c, float *out, long long B) {
@@ -163,6 +327,10 @@ static int digest(const ocd_params *p, KParams &k) {
     k.S = p->extra_inits ? 6 : 3;
     k.other_mode = p->other_mode;
     k.extra_inits = p->extra_inits ? 1 : 0;
+    if (p->optimizer != 0 && p->optimizer != 1) return OCD_EINVAL;
+    if (p->reserved != 0) return OCD_EINVAL;
+    if (p->optimizer == 1 && p->H > OCD_LBFGS_MAX_H) return OCD_EUNSUP;
+    k.optimizer = p->optimizer;
     k.lr = (float)p->lr;
     k.dt = (float)p->dt;
     k.dt2 = (float)(p->dt * p->dt);              // dt**2 in double, cast once (simulation_utils.py:16)
@@ -330,6 +498,12 @@ int ocd_solve_batch(const ocd_params *p, const float *world, const float *other_
     if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
     SolveArgs a{world, other_controls, Bo, weights, Bw, weight_idx, cur_speed, plan, losses, best, all_plans,
                 B, pick_P(B)};
+    if (k.optimizer == 1) {
+        const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, kP, false, false, false) * sizeof(float);
+        if ((rc = prepare_smem(k_solve_lbfgs, bytes))) return rc;
+        k_solve_lbfgs<<<(unsigned)((B + kP - 1) / kP), k.S * kP, bytes, (cudaStream_t)stream>>>(k, a);
+        return cuda_status();
+    }
     return launch_solve(k, p->math_mode == 1, a, (cudaStream_t)stream);
 }
 
@@ -344,6 +518,7 @@ int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc, const float *
     if (B == 0) return OCD_OK;
     if (!sc || !robot_init || !true_weights || !returns || B < 0 || T < 0 || t0 < 0) return OCD_EINVAL;
     if (sc->n_other != k.NO) return OCD_EINVAL;
+    if (k.optimizer != 0) return OCD_EUNSUP;      // the episode loop runs the reference's SGD planner only
     for (int j = 0; j < k.NO; ++j)
         if (sc->plan_len[j] < 0 || sc->plan_len[j] > OCD_MAX_PLAN || (sc->kind[j] != 0 && sc->kind[j] != 1))
             return OCD_EINVAL;

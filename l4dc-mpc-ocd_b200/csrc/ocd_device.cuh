@@ -34,7 +34,7 @@ namespace ocd {
 // Device-side digest of ocd_params: every Python-float constant already cast to float32 the
 // way TensorFlow casts it at op time.
 struct KParams {
-    int   H, NO, L, K, n_iter, S, other_mode, extra_inits;
+    int   H, NO, L, K, n_iter, S, other_mode, extra_inits, optimizer;
     float lr, dt, dt2, hdt2;      // dt2 = (float)(dt*dt) squared in double; hdt2 = 0.5f*dt2
     float mu, ts, bound;          // friction, target speed, 4*ts^2
     float thr_lo, thr_w, fshape;  // fence ramp: |x| in [thr_lo, thr_lo + thr_w], shape = 5/width

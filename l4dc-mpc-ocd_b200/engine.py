@@ -24,6 +24,7 @@ import torch
 from . import _native as N
 
 MATH_FAST, MATH_PRECISE = 0, 1
+OPT_SGD, OPT_LBFGS = 0, 1
 
 
 @dataclass
@@ -37,6 +38,7 @@ class PlannerParams:
     other_mode: int = 0            # 0: other cars keep velocity; 1: known controls
     extra_inits: bool = False
     math_mode: int = MATH_FAST
+    optimizer: int = OPT_SGD       # OPT_LBFGS: opt-in L-BFGS (H <= 16), n_iter = maximum iterations
     lr: float = 0.1
     dt: float = 0.1
     friction: float = 0.2
@@ -61,6 +63,7 @@ class PlannerParams:
         p.H, p.C, p.L, p.n_iter = int(self.H), int(self.C), self.L, int(self.n_iter)
         p.num_lanes, p.other_mode = int(self.num_lanes), int(self.other_mode)
         p.extra_inits, p.math_mode = int(bool(self.extra_inits)), int(self.math_mode)
+        p.optimizer, p.reserved = int(self.optimizer), 0
         p.lr, p.dt, p.friction, p.target_speed = float(self.lr), float(self.dt), float(self.friction), \
             float(self.target_speed)
         for i, x in enumerate(self.lane_x):

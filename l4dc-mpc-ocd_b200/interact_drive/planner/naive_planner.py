@@ -113,11 +113,16 @@ class NaivePlanner(CarPlanner):
         """-> list of H controls (2,) float32: the start with the smallest final loss after n_iter
         gradient steps (reference :81-164).  init_state None = the world's current state; weights None =
         the car's own normalised weights."""
-        if use_lbfgs:
-            raise NotImplementedError("use_lbfgs: the reference's TFP branch is never enabled by its drivers "
-                                      "(and mis-binds its arguments); the engine implements the SGD path")
         oc = self._other_controls(other_controls)
         p = self.params(other_mode=0 if oc is None else 1)
+        if use_lbfgs:
+            # The reference's branch (:127-149) hands each start to TFP's lbfgs_minimize with
+            # max_iterations=200; it is never enabled by its drivers and mis-binds `weights` as
+            # other_controls.  Here the flag selects the engine's own L-BFGS (same role, its own line
+            # search -- see include/ocd_b200.h), with the arguments bound as the SGD branch binds them.
+            if self.horizon > _eng.N.LBFGS_MAX_H:
+                raise NotImplementedError("use_lbfgs: the L-BFGS kernel supports horizon <= %d" % _eng.N.LBFGS_MAX_H)
+            p.optimizer, p.n_iter = _eng.OPT_LBFGS, 200
         cur_speed = [float(self.car.state[2])]                      # live speed, not init_state's (reference :114)
         res = self.engine.solve(p, self._world_array(init_state)[None], self._weights(weights),
                                 other_controls=None if oc is None else oc[None], cur_speed=cur_speed)

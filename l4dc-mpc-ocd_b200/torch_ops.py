@@ -30,14 +30,14 @@ def _engine(t: torch.Tensor) -> Engine:
 def pack_params(p: PlannerParams) -> List[float]:
     """PlannerParams -> flat list understood by the ops."""
     return [float(p.H), float(p.C), float(p.n_iter), float(p.num_lanes), float(p.other_mode), float(bool(p.extra_inits)),
-            float(p.math_mode), float(p.lr), float(p.dt), float(p.friction), float(p.target_speed)] + \
-        [float(x) for x in p.lane_x]
+            float(p.math_mode), float(p.lr), float(p.dt), float(p.friction), float(p.target_speed),
+            float(p.optimizer)] + [float(x) for x in p.lane_x]
 
 
 def unpack_params(v: List[float]) -> PlannerParams:
     return PlannerParams(H=int(v[0]), C=int(v[1]), n_iter=int(v[2]), num_lanes=int(v[3]), other_mode=int(v[4]),
                          extra_inits=bool(v[5]), math_mode=int(v[6]), lr=v[7], dt=v[8], friction=v[9],
-                         target_speed=v[10], lane_x=tuple(v[11:]))
+                         target_speed=v[10], optimizer=int(v[11]), lane_x=tuple(v[12:]))
 
 
 @torch.library.custom_op("ocd_b200::solve", mutates_args=())

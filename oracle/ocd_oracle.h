@@ -38,6 +38,9 @@ extern "C" {
 #define OCDO_MAX_PLAN  16
 #define OCDO_MAX_H     64
 #define OCDO_MAX_S     6
+#define OCDO_LBFGS_M   4     /* correction pairs                                        */
+#define OCDO_LBFGS_LS  6     /* backtracking trials                                     */
+#define OCDO_LBFGS_MAX_H 16
 
 /* Planner / world constants.  Doubles here; the _f32 functions cast each one to float at
  * the point of use, which is what TF does with Python-float constants. */
@@ -49,7 +52,7 @@ typedef struct {
     int32_t num_lanes;   /* fence threshold = 0.05*num_lanes       merging.py:80           */
     int32_t other_mode;  /* 0 constant velocity, 1 known controls  naive_planner.py:53-66  */
     int32_t extra_inits; /* 3 extra starts with a0 = mu*v^2        naive_planner.py:112-116*/
-    int32_t _pad;
+    int32_t optimizer;   /* 0 SGD (the reference); 1 the engine's opt-in L-BFGS (no reference counterpart that runs) */
     double  lr;          /* SGD learning rate                      naive_planner.py:28     */
     double  dt;          /* world.dt                               world.py:18             */
     double  friction;    /* robot friction                         car.py:33               */

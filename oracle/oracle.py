@@ -28,7 +28,7 @@ class _Params(C.Structure):
     _fields_ = [
         ("H", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("n_iter", C.c_int32),
         ("num_lanes", C.c_int32), ("other_mode", C.c_int32), ("extra_inits", C.c_int32),
-        ("_pad", C.c_int32),
+        ("optimizer", C.c_int32),
         ("lr", C.c_double), ("dt", C.c_double), ("friction", C.c_double),
         ("target_speed", C.c_double), ("lane_x", C.c_double * MAX_LANES),
     ]
@@ -59,6 +59,7 @@ class OracleParams:
     dt: float = 0.1
     friction: float = 0.2
     target_speed: float = 1.0
+    optimizer: int = 0            # 1: the engine's opt-in L-BFGS (no running reference counterpart)
 
     @property
     def L(self) -> int:
@@ -76,6 +77,7 @@ class OracleParams:
         p = _Params()
         p.H, p.C, p.L, p.n_iter = self.H, self.C, self.L, self.n_iter
         p.num_lanes, p.other_mode, p.extra_inits = self.num_lanes, self.other_mode, int(self.extra_inits)
+        p.optimizer = int(self.optimizer)
         p.lr, p.dt, p.friction, p.target_speed = self.lr, self.dt, self.friction, self.target_speed
         for i, x in enumerate(self.lane_x):
             p.lane_x[i] = float(x)

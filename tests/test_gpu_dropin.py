@@ -107,6 +107,17 @@ def test_friction_correct_speed():             # reference :50-63
     np.testing.assert_allclose(np.stack(plan), kat["plan"], atol=5e-5)
 
 
+def test_use_lbfgs_reaches_the_known_answers():
+    """generate_plan(use_lbfgs=True): the engine's L-BFGS on the same two known-answer problems."""
+    world = ThreeLaneCarWorld()
+    car = TargetSpeedPlannerCar(world, np.array([0., 0., 1., np.pi / 2], np.float32), 4, target_speed=1., friction=0.5)
+    world.add_car(car)
+    planner = NaivePlanner(world, car, horizon=3, learning_rate=5.0, n_iter=500)
+    plan = planner.generate_plan([car.state], use_lbfgs=True)
+    np.testing.assert_allclose(np.stack(plan)[:, 0], [0.5] * 3, atol=1e-4)
+    assert float(planner.last_losses[planner.last_best]) <= 1e-9
+
+
 def test_no_interaction():                     # reference :76-96 (other_controls path; plus a value check)
     world = ThreeLaneCarWorld()
     car = TargetSpeedPlannerCar(world, np.array([0., 0., 1., np.pi / 2], np.float32), 4, friction=0.)
@@ -127,7 +138,7 @@ def test_planner_rejects_unsupported():
     car = TargetSpeedPlannerCar(world, np.array([0., 0., 1., np.pi / 2], np.float32), 4)
     world.add_car(car)
     with pytest.raises(NotImplementedError):
-        NaivePlanner(world, car, 5).generate_plan(use_lbfgs=True)
+        NaivePlanner(world, car, 17).generate_plan(use_lbfgs=True)       # L-BFGS kernel: horizon <= 16
     with pytest.raises(NotImplementedError):
         NaivePlanner(world, car, 5, leaf_evaluation=lambda s, u: 0)
     with pytest.raises(TypeError):
