@@ -30,6 +30,18 @@ OCD_EXTERN(0, 1, 3)   // any horizon, one other car, three lanes: segmented adjo
 OCD_EXTERN(0, 0, 3)   // any horizon / cars on three lanes: segmented adjoint
 OCD_EXTERN(0, 0, 0)   // any other shape: runtime H, cars, lanes (segmented adjoint)
 #undef OCD_EXTERN
+// FAST k_solve alone, compile-time car count: the 3..6-car points of the synthetic sweep
+#define OCD_EXTERN_SOLVE(HT, NO, LT) \
+    extern template int launch_solve_t<HT, NO, LT, false>(const KParams &, const SolveArgs &, cudaStream_t);
+OCD_EXTERN_SOLVE(5, 2, 3)
+OCD_EXTERN_SOLVE(5, 3, 3)
+OCD_EXTERN_SOLVE(5, 4, 3)
+OCD_EXTERN_SOLVE(5, 5, 3)
+OCD_EXTERN_SOLVE(0, 2, 3)
+OCD_EXTERN_SOLVE(0, 3, 3)
+OCD_EXTERN_SOLVE(0, 4, 3)
+OCD_EXTERN_SOLVE(0, 5, 3)
+#undef OCD_EXTERN_SOLVE
 
 // ---------------------------------------------------------------------------------------------
 // operator kernels: reward + gradient, features, dynamics
@@ -379,6 +391,15 @@ static int pick_P(long long) { return kP; }
 
 static int launch_solve(const KParams &k, bool precise, const SolveArgs &a, cudaStream_t st) {
     if (precise) OCD_DISPATCH(launch_solve_t, true, k, a, st);
+    if (k.L == 3 && k.NO >= 2 && k.NO <= 5) {
+        const bool h5 = k.H == 5;
+        switch (k.NO) {
+            case 2: return h5 ? launch_solve_t<5, 2, 3, false>(k, a, st) : launch_solve_t<0, 2, 3, false>(k, a, st);
+            case 3: return h5 ? launch_solve_t<5, 3, 3, false>(k, a, st) : launch_solve_t<0, 3, 3, false>(k, a, st);
+            case 4: return h5 ? launch_solve_t<5, 4, 3, false>(k, a, st) : launch_solve_t<0, 4, 3, false>(k, a, st);
+            default: return h5 ? launch_solve_t<5, 5, 3, false>(k, a, st) : launch_solve_t<0, 5, 3, false>(k, a, st);
+        }
+    }
     OCD_DISPATCH(launch_solve_t, false, k, a, st);
 }
 

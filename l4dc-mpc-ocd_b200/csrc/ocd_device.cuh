@@ -344,8 +344,8 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         // hx, hy below are d(val)/d(position) without the constant -2/half-width (folded into
         // wcx, wcy).  A warp with every lane outside every support skips the transcendental part.
         float hx = 0.0f, hy = 0.0f;
-        if (NOT_ > 0) {
-            // compile-time car count (the shipped scenarios): value and derivatives per car, TF's even
+        if (NOT_ == 1 || NOT_ == 2) {
+            // one or two other cars (the shipped scenarios): value and derivatives per car, TF's even
             // split among exact ties applied on the fly (the replanning scenario's two other cars start
             // on top of each other, so exact ties are the normal case there)
             float best = 0.0f, cnt = 1.0f;
@@ -378,33 +378,44 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 hy *= r;
             }
         } else {
-            // runtime car count (sweeps with many cars): only the VALUE is computed per car; the winner's
-            // offsets and reciprocals ride along through selects and its derivatives are formed once, after
-            // the loop.  Fully unrolled with uniform guards, so every slab address is an immediate.  An exact
-            // tie between two non-zero values (measure zero, but TF splits the gradient there) is flagged and
-            // sends the warp through the exact rule.
-            float best = 0.0f, bnx = 0.0f, bny = 0.0f, brx = 0.0f, bry = 0.0f;
+            // three or more other cars, or a runtime count (sweeps with many cars).  bx*by =
+            // exp(2 - 1/ux - 1/uy) with u = 1 - n^2 is monotone in 1/ux + 1/uy = (ux + uy)/(ux uy), so the
+            // maximum over cars is an argmin of that score: ONE reciprocal per car and no exponential; the
+            // winner's offsets ride along through two selects and its value and derivatives are formed once,
+            // after the loop (3 more MUFU).  Outside the support u is clamped to a tiny positive number -- a
+            // different one per car, so that two far cars never produce equal scores -- and the score is
+            // >= 1e5: the exponential underflows to exactly 0.  Fully unrolled (with uniform guards when the
+            // count is a runtime value), so every slab address and clamp is an immediate.
+            // Ties: an exact tie of two scores inside the support (cars at the same spot, or the robot dead
+            // centre between two cars -- TF splits the gradient there) sets a sticky flag and sends the warp
+            // through the exact rule below.
+            float bsum = 3.0e38f, bnx = 0.0f, bny = 0.0f;
             bool tie = false;
 #pragma unroll
-            for (int j = 0; j < OCD_MAX_OTHER; ++j) {
-                if (j >= NO) break;
+            for (int j = 0; j < (NOT_ > 0 ? NOT_ : OCD_MAX_OTHER); ++j) {
+                if (NOT_ == 0 && j >= NO) break;
                 const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
                 const float cyj = LIN ? fmaf(tf, oth[j * jstride + 3 * cstride], oth[j * jstride + 2 * cstride])
                                       : oth[j * jstride + cstride];
                 const float nx = fmaf(x, OCD_BUMP_IX, -cxj);
                 const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
-                const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
-                if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
-                    const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
-                    const float val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
-                    tie = tie || (val == best && val > 0.0f);
-                    const bool gt = val > best;
-                    best = fmaxf(best, val);
-                    bnx = gt ? nx : bnx; bny = gt ? ny : bny; brx = gt ? rx : brx; bry = gt ? ry : bry;
-                }
+                const float eps = 1e-6f * (1.0f + 0.125f * (float)j);
+                const float ux = fmaxf(fmaf(-nx, nx, 1.0f), eps), uy = fmaxf(fmaf(-ny, ny, 1.0f), eps);
+                const float sum = (ux + uy) * Mth<false>::rcp_(ux * uy);
+                tie = tie || (sum == bsum);
+                const bool lt = sum < bsum;
+                bsum = fminf(bsum, sum);
+                bnx = lt ? nx : bnx;
+                bny = lt ? ny : bny;
             }
-            hx = (best * bnx) * (brx * brx);
-            hy = (best * bny) * (bry * bry);
+            tie = tie && bsum < 1.0e5f;
+            if (__any_sync(OCD_FULL, bsum < 1.0e5f)) {
+                const float rx = Mth<false>::rcp_(fmaxf(fmaf(-bnx, bnx, 1.0f), 1e-6f));
+                const float ry = Mth<false>::rcp_(fmaxf(fmaf(-bny, bny, 1.0f), 1e-6f));
+                const float best = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
+                hx = (best * bnx) * (rx * rx);
+                hy = (best * bny) * (ry * ry);
+            }
             if (__any_sync(OCD_FULL, tie)) {
                 float b2 = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
                 for (int j = 0; j < NO; ++j) {
