@@ -273,8 +273,10 @@ __device__ __forceinline__ float lane_min_offset_exact(const KParams &k, float x
 // FAST: the nearest lane by |x - l_i| (no feature values needed); feature values can only tie when
 // x sits within rounding of a midpoint between two neighbouring lanes, and only then -- decided by a
 // warp vote, so normally one uniform branch -- the exact rule above runs.
-template <int LT, bool PRECISE>
-__device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
+// VM (vote mode) 1 -- the straight-line variant of the latency kernels -- only reports `close` through
+// `flag`; the caller re-runs the step with the exact rule when any lane raised it.
+template <int LT, bool PRECISE, int VM = 0>
+__device__ __forceinline__ float lane_min_offset(const KParams &k, float x, bool &flag) {
     if (PRECISE) return lane_min_offset_exact<LT>(k, x);
     const int L = LT > 0 ? LT : k.L;
     float dsel = x - k.lane_x[0];
@@ -287,6 +289,10 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
             near = fminf(near, fabsf(x - k.lane_mid[i - 1]));
         }
     const bool close = near < 1e-6f;
+    if (VM == 1) {
+        flag = flag || close;
+        return dsel;
+    }
     if (__any_sync(OCD_FULL, close)) {        // whole warp takes the exact rule: no divergence to reconverge
         const float exact = lane_min_offset_exact<LT>(k, x);
         dsel = close ? exact : dsel;
@@ -300,10 +306,13 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x) {
 // (x0, dx, y0, dy) per car -- four rows, car stride jstride = 4*cstride -- and the position after
 // tf steps is x0 + tf*dx.  That keeps the slab independent of H, which is what lets long horizons with
 // many cars keep several blocks per SM.
-template <int NOT_, int LT, bool PRECISE, bool LIN = false>
+// VM = 1 (FAST only): no warp votes and no rare-path branches -- every block below is computed
+// unconditionally (the clamped formulations make that safe), so the whole horizon is one basic block the
+// scheduler can interleave; whatever needs an exact rule (lane tie, collision tie) raises `flag` instead.
+template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
-                                             float &gx, float &gy, float &gv, float &gth, float tf = 0.0f) {
+                                             float &gx, float &gy, float &gv, float &gth, float tf, bool &flag) {
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
     // speed: min((v sin th - ts)^2, 4 ts^2)                                  merging.py:58-59
     {
@@ -313,7 +322,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         gth = (ke * v) * cs;
     }
     // lanes: sum_i w_i 10 (x - l_i)^2 and the min over lanes                 merging.py:61-65
-    gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE>(k, x), fmaf(w.GA, x, w.GB));
+    gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE, VM>(k, x, flag), fmaf(w.GA, x, w.GB));
     // collision: max_j bump_x * bump_y                                        merging.py:67-78
     if (PRECISE) {
         float best = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
@@ -358,7 +367,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 const float ny = fmaf(y, OCD_BUMP_IY, -cyj);
                 const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
                 float val = 0.0f, vx = 0.0f, vy = 0.0f;
-                if (__any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
+                if (VM == 1 || __any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
                     const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
                     val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
                     vx = (val * nx) * (rx * rx);
@@ -372,8 +381,8 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                     hx += vx; hy += vy; cnt += 1.0f;
                 }
             }
-            if (NOT_ != 1 && cnt != 1.0f) {
-                const float r = __fdiv_rn(1.0f, cnt);
+            if (NOT_ != 1) {                     // cnt is 1 or 2 here: 1/cnt without a division or a branch
+                const float r = (cnt != 1.0f) ? 0.5f : 1.0f;
                 hx *= r;
                 hy *= r;
             }
@@ -409,14 +418,15 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 bny = lt ? ny : bny;
             }
             tie = tie && bsum < 1.0e5f;
-            if (__any_sync(OCD_FULL, bsum < 1.0e5f)) {
+            if (VM == 1 || __any_sync(OCD_FULL, bsum < 1.0e5f)) {
                 const float rx = Mth<false>::rcp_(fmaxf(fmaf(-bnx, bnx, 1.0f), 1e-6f));
                 const float ry = Mth<false>::rcp_(fmaxf(fmaf(-bny, bny, 1.0f), 1e-6f));
                 const float best = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
                 hx = (best * bnx) * (rx * rx);
                 hy = (best * bny) * (ry * ry);
             }
-            if (__any_sync(OCD_FULL, tie)) {
+            if (VM == 1) flag = flag || tie;
+            if (VM != 1 && __any_sync(OCD_FULL, tie)) {
                 float b2 = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
                 for (int j = 0; j < NO; ++j) {
                     const float cxj = LIN ? fmaf(tf, oth[j * jstride + cstride], oth[j * jstride]) : oth[j * jstride];
@@ -451,7 +461,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 fence_inside<true>(k, x, ax, q, f, df);
                 gx = fmaf(w.wfence, df, gx);
             }
-        } else if (__any_sync(OCD_FULL, q > 0.0f)) {
+        } else if (VM == 1 || __any_sync(OCD_FULL, q > 0.0f)) {
             // T = F1/(F1+F2) = 1/(1 + exp(r1 - r2)), r1 = 1/(shape q), r2 = 1/(shape (width - q));
             // dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping q and width-q to a tiny positive number
             // makes the exponential saturate: T = 0, dT = 0 below the ramp and T = 1, dT = 0 above it,
@@ -553,15 +563,15 @@ struct SmemTraj {
 __host__ __device__ inline int seg_u_stride(int H) { return (2 * H) | 1; }
 __host__ __device__ inline int seg_ck_stride(int H, int SEG) { return (4 * ((H + SEG - 1) / SEG)) | 1; }
 
-template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE>
-__device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
+// Forward half of one iteration: roll the robot out and, at every new state, take the gradient of w.phi.
+// Fills the saved per-step values the reverse sweep needs.  VM as in feature_grad.
+template <int HT, int NOT_, int LT, bool PRECISE, int VM>
+__device__ __forceinline__ void forward_sweep(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                               float th0, float sn0, float cs0, const float *oth, int P,
-                                              Traj<HT> &u, float *ga_out, float *gw_out) {
-    constexpr int HM = Traj<HT>::HM;
+                                              const Traj<HT> &u, float *sv, float *sc, float *ss, float *sd,
+                                              float *gx, float *gy, float *gv, float *gth, bool &flag) {
     const int H = HT > 0 ? HT : k.H;
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
-    float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
-    float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
     float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
@@ -575,8 +585,32 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
         v = fmaf(total, k.dt, v);
         th = fmaf(oc, k.dt, th);
         Mth<PRECISE>::sincos_(th, sn, cs);
-        feature_grad<NOT_, LT, PRECISE>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
-                                        gx[t], gy[t], gv[t], gth[t]);
+        feature_grad<NOT_, LT, PRECISE, false, VM>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
+                                                   gx[t], gy[t], gv[t], gth[t], 0.0f, flag);
+    }
+}
+
+// LAT: the latency variant for small batches (few warps per SM, nothing to hide latency with): the forward
+// sweep is straight-line code -- no votes, no rare-path branches -- and is simply run again with the exact
+// rules in the rare case that some lane needed one.
+template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE, bool LAT = false>
+__device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
+                                              float th0, float sn0, float cs0, const float *oth, int P,
+                                              Traj<HT> &u, float *ga_out, float *gw_out) {
+    constexpr int HM = Traj<HT>::HM;
+    const int H = HT > 0 ? HT : k.H;
+    float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
+    float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
+    bool flag = false;
+    if (LAT && !PRECISE) {
+        forward_sweep<HT, NOT_, LT, PRECISE, 1>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, sd, gx, gy, gv,
+                                                gth, flag);
+        if (__any_sync(OCD_FULL, flag))
+            forward_sweep<HT, NOT_, LT, PRECISE, 0>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, sd, gx, gy,
+                                                    gv, gth, flag);
+    } else {
+        forward_sweep<HT, NOT_, LT, PRECISE, 0>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, sd, gx, gy, gv,
+                                                gth, flag);
     }
     float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
@@ -647,7 +681,7 @@ __device__ __forceinline__ void init_start(const KParams &k, int s, float cur_sp
 }
 
 // The complete solve for one (problem, start): n_iter SGD iterations, then the final loss.
-template <int HT, int NOT_, int LT, bool PRECISE>
+template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
 __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, const float *wraw, int ws,
                                              float x0, float y0, float v0, float th0, const float *oth, int P,
                                              Traj<HT> &u) {
@@ -655,7 +689,7 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
     Mth<PRECISE>::sincos_(th0, sn0, cs0);
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
-        sgd_iteration<HT, NOT_, LT, PRECISE, true>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
+        sgd_iteration<HT, NOT_, LT, PRECISE, true, LAT>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
     return -rollout_reward<HT, LT, PRECISE, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 
@@ -729,8 +763,9 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
                 v = fmaf(total, k.dt, v);
                 th = fmaf(oc, k.dt, th);
                 Mth<PRECISE>::sincos_(th, sn, cs);
+                bool unused = false;
                 feature_grad<NOT_, LT, PRECISE, LIN>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P, gx[i], gy[i],
-                                                     gv[i], gth[i], tbase + (float)(i + 1));
+                                                     gv[i], gth[i], tbase + (float)(i + 1), unused);
             }
         }
 #pragma unroll

@@ -143,8 +143,10 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // ---------------------------------------------------------------------------------------------
 // k_solve
 // ---------------------------------------------------------------------------------------------
-template <int HT, int NOT_, int LT, bool PRECISE>
-__global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4) k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
+// LAT: the latency variant (straight-line forward sweep, see sgd_iteration), launched for small batches.
+template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
+__global__ void __launch_bounds__(kMaxThreads, LAT ? 1 : (HT == 0 ? 3 : 4))
+k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
     constexpr bool SEGK = (HT == 0);     // runtime horizon: segmented adjoint, controls in shared memory
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4) k_solve(const __
                                                                      s, speed, us, ck);
     } else {
         init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
-        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
+        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
+                                                                      u);
     }
     m.loss[s * P + p] = loss;
     if (live) {
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4) k_solve(const __
 // ---------------------------------------------------------------------------------------------
 // k_episode
 // ---------------------------------------------------------------------------------------------
-template <int HT, int NOT_, int LT, bool PRECISE>
-__global__ void __launch_bounds__(kMaxThreads, HT == 0 ? 3 : 4)
+template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
+__global__ void __launch_bounds__(kMaxThreads, LAT ? 1 : (HT == 0 ? 3 : 4))
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;
@@ -306,8 +309,8 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
                                                                          m.oth + p, P, s, v0, us, ck);
         } else {
             init_start<(HT > 0 ? HT : 1)>(k, s, v0, u);
-            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p,
-                                                                      P, u);
+            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                           m.oth + p, P, u);
         }
         m.loss[s * P + p] = loss;
         m.u0[(s * 2 + 0) * P + p] = SEGK ? us.acc(0) : u.acc(0);
@@ -366,11 +369,17 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
+// A batch is "small" when its warps cannot hide each other's latency: at most two per SM sub-partition
+// of a 148-SM part.  The compile-time-horizon FAST kernels then run their latency variant.
+inline bool small_batch(long long B, int P, int S) { return ((B + P - 1) / P) * S <= 2 * 4 * 148; }
+
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
+    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
+    if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
@@ -382,7 +391,9 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
+    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
+    if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);

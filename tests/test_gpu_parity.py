@@ -177,7 +177,10 @@ def test_generate_plan_golden_scenarios(engine, mode, _n):
     (5, 2, 3, 0, False, 100, 0.1), (5, 3, 2, 1, False, 100, 0.1), (6, 2, 3, 0, False, 200, 0.1),
     (5, 2, 3, 0, True, 100, 0.1), (3, 4, 3, 0, False, 60, 0.1), (8, 2, 3, 0, False, 50, 0.1),
     (15, 3, 3, 1, False, 40, 0.01), (5, 5, 3, 0, False, 100, 0.1), (15, 2, 3, 0, False, 100, 0.03),
-    (50, 2, 3, 0, False, 20, 0.003), (50, 6, 3, 0, False, 10, 0.003)])
+    (50, 2, 3, 0, False, 20, 0.003), (50, 6, 3, 0, False, 10, 0.003),
+    # every compile-time car count of the sweep specialisations (k_solve<5|0, 2..5, 3, fast>)
+    (5, 3, 3, 0, False, 100, 0.1), (5, 4, 3, 0, False, 100, 0.1), (5, 6, 3, 0, False, 100, 0.1),
+    (15, 4, 3, 0, False, 40, 0.03), (15, 5, 3, 1, False, 40, 0.03), (15, 6, 3, 0, False, 40, 0.03)])
 def test_generate_plan_random_vs_oracle(engine, mode, _n, H, C, lanes, other_mode, extra, n_iter, lr):
     """Fixed-budget gradient ascent is an iterated map: on a few random problems it is unstable and
     even the float32 and float64 oracles disagree.  Parity is asserted where the reference itself
