@@ -311,7 +311,7 @@ def main():
                        "d2h_bytes_per_step": int(r["plan"].nbytes + r["losses"].nbytes + r["best"].nbytes),
                        "steps": ke, "ms_per_step": 1e3 * t_e2e / ke,
                        "api": "ocd_solve_batch_host: pinned host arrays in, pinned host arrays out, "
-                              "chunked over 3 streams so copies overlap the solve",
+                              "ramped column chunks over an H2D stream, two compute lanes and a D2H stream, so copies overlap the solve",
                        "pageable_host_arrays_value": B * world_size / t_pageable}
         line["gpu_launches"] = launches
         ctx.close()

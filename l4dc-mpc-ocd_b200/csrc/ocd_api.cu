@@ -551,7 +551,7 @@ int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc, const float *
 }
 
 // ---- host-buffer layer ------------------------------------------------------------------------
-static constexpr int kCtxStreams = 3;
+static constexpr int kCtxStreams = 4;     // H2D, two compute lanes, D2H
 static constexpr int kMaxChunks = 16;
 
 struct ocd_ctx {
@@ -559,6 +559,8 @@ struct ocd_ctx {
     cudaStream_t stream;                 // small calls (episodes)
     cudaStream_t lanes[kCtxStreams];     // the chunk pipeline of ocd_solve_batch_host
     cudaEvent_t ready;                   // shared inputs (weights) are on the device
+    cudaEvent_t loaded[kMaxChunks];      // chunk c's inputs are on the device
+    cudaEvent_t solved[kMaxChunks];      // chunk c's kernel has finished
     cudaEvent_t done[kMaxChunks];        // chunk c's outputs are in host memory
     char *dev;      size_t dev_cap;
     char *pin;      size_t pin_cap;
@@ -593,7 +595,9 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
         ok = ok && cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kMaxChunks; ++i)
-        ok = ok && cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->loaded[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->solved[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         delete c;
@@ -611,7 +615,11 @@ void ocd_ctx_destroy(ocd_ctx *c) {
     cudaStreamDestroy(c->stream);
     for (int i = 0; i < kCtxStreams; ++i) cudaStreamDestroy(c->lanes[i]);
     cudaEventDestroy(c->ready);
-    for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(c->done[i]);
+    for (int i = 0; i < kMaxChunks; ++i) {
+        cudaEventDestroy(c->done[i]);
+        cudaEventDestroy(c->loaded[i]);
+        cudaEventDestroy(c->solved[i]);
+    }
     delete c;
 }
 
@@ -636,6 +644,47 @@ static bool is_pinned(const void *ptr) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Column chunks of the host-buffer solve: start[0..n] with start[n] = B, every boundary a multiple of 64
+// problems (256-byte aligned rows).  Small batches are one chunk.  Large ones ramp up and down -- weights
+// 1,2,4,6,...,6,4,2,1 -- so that the first kernel starts after a short copy and only a short copy is left
+// when the last kernel ends, while the middle chunks are several full waves each.
+// OCD_HOST_CHUNKS="w0,w1,..." overrides the weights (tuning knob, read at every call).
+static int chunk_schedule(int64_t B, int64_t *start) {
+    int w[kMaxChunks], n = 0;
+    if (const char *e = std::getenv("OCD_HOST_CHUNKS")) {
+        for (const char *q = e; *q && n < kMaxChunks;) {
+            char *end;
+            const long v = std::strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0) w[n++] = (int)v;
+            q = (*end == ',') ? end + 1 : end;
+        }
+    }
+    if (n == 0) {
+        if (B <= 65536) {
+            w[n++] = 1;
+        } else if (B <= 262144) {
+            for (int i = 0; i < 4; ++i) w[n++] = 1;
+        } else {
+            const int ramp[] = {1, 2, 4, 6, 6, 6, 4, 2, 1};
+            for (int v : ramp) w[n++] = v;
+        }
+    }
+    int64_t tot = 0;
+    for (int i = 0; i < n; ++i) tot += w[i];
+    int64_t acc = 0;
+    int m = 0;
+    start[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        acc += w[i];
+        int64_t e = (i == n - 1) ? B : ((B * acc / tot) + 63) / 64 * 64;
+        if (e > B) e = B;
+        if (e > start[m]) start[++m] = e;
+    }
+    if (start[m] != B) start[++m] = B;
+    return m;
+}
+
 // One [rows][B] host array moved in column chunks.  Pinned user memory is copied in place (a
 // strided 2-D copy); pageable memory goes through the context's pinned staging area.
 struct HostArray {
@@ -646,16 +695,15 @@ struct HostArray {
     size_t dev_off, pin_off;    // per-chunk compact [rows][n] buffers in the device / pinned arena
 };
 
-static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk,
-                     cudaStream_t st) {
+static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, cudaStream_t st) {
     if (!a.user) return OCD_OK;
-    char *dst = c->dev + a.dev_off + (size_t)chunk * a.rows * cap * a.elem;
+    char *dst = c->dev + a.dev_off + (size_t)a.rows * b0 * a.elem;     // chunks are packed back to back
     cudaError_t e;
     if (a.pinned) {
         e = cudaMemcpy2DAsync(dst, n * a.elem, a.user + b0 * a.elem, B * a.elem, n * a.elem, a.rows,
                               cudaMemcpyHostToDevice, st);
     } else {
-        char *stage = c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem;
+        char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
         for (int r = 0; r < a.rows; ++r)
             std::memcpy(stage + (size_t)r * n * a.elem, a.user + ((size_t)r * B + b0) * a.elem, n * a.elem);
         e = cudaMemcpyAsync(dst, stage, (size_t)a.rows * n * a.elem, cudaMemcpyHostToDevice, st);
@@ -663,29 +711,30 @@ static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
     return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
 }
 
-static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk,
-                     cudaStream_t st) {
-    const char *src = c->dev + a.dev_off + (size_t)chunk * a.rows * cap * a.elem;
+static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, cudaStream_t st) {
+    const char *src = c->dev + a.dev_off + (size_t)a.rows * b0 * a.elem;
     cudaError_t e;
     if (a.pinned)
         e = cudaMemcpy2DAsync(a.user + b0 * a.elem, B * a.elem, src, n * a.elem, n * a.elem, a.rows,
                               cudaMemcpyDeviceToHost, st);
     else
-        e = cudaMemcpyAsync(c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem, src,
+        e = cudaMemcpyAsync(c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem, src,
                             (size_t)a.rows * n * a.elem, cudaMemcpyDeviceToHost, st);
     return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
 }
 
-static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, int64_t cap, int chunk) {
+static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n) {
     if (a.pinned) return;
-    const char *stage = c->pin + a.pin_off + (size_t)chunk * a.rows * cap * a.elem;
+    const char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
     for (int r = 0; r < a.rows; ++r)
         std::memcpy(a.user + ((size_t)r * B + b0) * a.elem, stage + (size_t)r * n * a.elem, n * a.elem);
 }
 
-// The batch is cut into column chunks that flow through three streams: while chunk i is being
-// solved, chunk i+1 is on its way to the device and chunk i-1 on its way back, so that the call
-// costs about max(copy, solve) instead of their sum.
+// The batch is cut into column chunks that flow through four streams linked by per-chunk events: one
+// stream feeds the H2D copy engine (running ahead as far as it can -- every chunk has its own device
+// buffers), two compute lanes take the chunks alternately (so that one kernel's tail wave is filled by the
+// next kernel's blocks), one stream drains results through the D2H copy engine.  The SMs never wait for
+// a copy after the first chunk and the call costs about max(copy, solve) instead of their sum.
 int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
                          int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
                          const float *cur_speed, float *plan, float *losses, int32_t *best, int64_t B) {
@@ -701,10 +750,8 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     const bool per_problem_w = !weight_idx && Bw == B && B > 1;     // weights travel with the chunks
     const bool per_problem_oc = k.other_mode == 1 && Bo == B && B > 1;
 
-    int nchunks = (int)((B + 65535) / 65536);
-    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
-    const int64_t cap = (((B + nchunks - 1) / nchunks) + 63) / 64 * 64;      // problems per chunk
-    nchunks = (int)((B + cap - 1) / cap);
+    int64_t start[kMaxChunks + 1];
+    const int nchunks = chunk_schedule(B, start);
 
     HostArray a_world{(char *)world, C * 4, 4, is_pinned(world), 0, 0};
     HostArray a_idx{(char *)weight_idx, 1, 4, is_pinned(weight_idx), 0, 0};
@@ -718,31 +765,40 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     Arena dev, pin;
     for (HostArray *a : arrays)
         if (a->user) {
-            a->dev_off = dev.take((size_t)nchunks * a->rows * cap * a->elem);
-            if (!a->pinned) a->pin_off = pin.take((size_t)nchunks * a->rows * cap * a->elem);
+            a->dev_off = dev.take((size_t)a->rows * B * a->elem);
+            if (!a->pinned) a->pin_off = pin.take((size_t)a->rows * B * a->elem);
         }
-    // shared (not per-problem) inputs: copied once, in full
-    const size_t n_w = per_problem_w ? 0 : sizeof(float) * k.K * Bw, o_w = dev.take(n_w), s_w = pin.take(n_w);
+    // shared (not per-problem) inputs: copied once, in full -- straight from the user's array when it is
+    // page-locked, through the staging area otherwise
+    const size_t n_w = per_problem_w ? 0 : sizeof(float) * k.K * Bw;
     const size_t n_oc = (k.other_mode == 1 && !per_problem_oc) ? sizeof(float) * k.NO * k.H * 2 * Bo : 0;
-    const size_t o_oc = dev.take(n_oc), s_oc = pin.take(n_oc);
+    const bool pin_w = n_w && is_pinned(weights), pin_oc = n_oc && is_pinned(other_controls);
+    const size_t o_w = dev.take(n_w), s_w = pin.take(pin_w ? 0 : n_w);
+    const size_t o_oc = dev.take(n_oc), s_oc = pin.take(pin_oc ? 0 : n_oc);
     if ((rc = ctx_reserve(c, dev.off, pin.off))) return rc;
-    if (n_w) std::memcpy(c->pin + s_w, weights, n_w);
-    if (n_oc) std::memcpy(c->pin + s_oc, other_controls, n_oc);
-    cudaStream_t s0 = c->lanes[0];
-    if (n_w && cudaMemcpyAsync(c->dev + o_w, c->pin + s_w, n_w, cudaMemcpyHostToDevice, s0) != cudaSuccess) return OCD_ECUDA;
-    if (n_oc && cudaMemcpyAsync(c->dev + o_oc, c->pin + s_oc, n_oc, cudaMemcpyHostToDevice, s0) != cudaSuccess) return OCD_ECUDA;
+    if (n_w && !pin_w) std::memcpy(c->pin + s_w, weights, n_w);
+    if (n_oc && !pin_oc) std::memcpy(c->pin + s_oc, other_controls, n_oc);
+    cudaStream_t s0 = c->lanes[0];        // the H2D stream: chunk copies are ordered behind the shared inputs
+    if (n_w && cudaMemcpyAsync(c->dev + o_w, pin_w ? (const char *)weights : c->pin + s_w, n_w, cudaMemcpyHostToDevice,
+                               s0) != cudaSuccess)
+        return OCD_ECUDA;
+    if (n_oc && cudaMemcpyAsync(c->dev + o_oc, pin_oc ? (const char *)other_controls : c->pin + s_oc, n_oc,
+                                cudaMemcpyHostToDevice, s0) != cudaSuccess)
+        return OCD_ECUDA;
     if (cudaEventRecord(c->ready, s0) != cudaSuccess) return OCD_ECUDA;
 
     auto chunk_ptr = [&](const HostArray &a, int ch) -> char * {
-        return a.user ? c->dev + a.dev_off + (size_t)ch * a.rows * cap * a.elem : nullptr;
+        return a.user ? c->dev + a.dev_off + (size_t)a.rows * start[ch] * a.elem : nullptr;
     };
+    cudaStream_t s_in = c->lanes[0], s_out = c->lanes[3];
     for (int ch = 0; ch < nchunks && rc == OCD_OK; ++ch) {
-        const int64_t b0 = (int64_t)ch * cap, n = (b0 + cap <= B) ? cap : B - b0;
-        cudaStream_t st = c->lanes[ch % kCtxStreams];
-        if (cudaStreamWaitEvent(st, c->ready, 0) != cudaSuccess) { rc = OCD_ECUDA; break; }
+        const int64_t b0 = start[ch], n = start[ch + 1] - b0;
+        cudaStream_t st = c->lanes[1 + (ch & 1)];
         for (HostArray *a : {&a_world, &a_idx, &a_w, &a_oc, &a_cs})
-            if (rc == OCD_OK) rc = h2d_chunk(c, *a, B, b0, n, cap, ch, st);
+            if (rc == OCD_OK) rc = h2d_chunk(c, *a, B, b0, n, s_in);
         if (rc) break;
+        if (cudaEventRecord(c->loaded[ch], s_in) != cudaSuccess ||
+            cudaStreamWaitEvent(st, c->loaded[ch], 0) != cudaSuccess) { rc = OCD_ECUDA; break; }
         rc = ocd_solve_batch(p, (const float *)chunk_ptr(a_world, ch),
                              per_problem_oc ? (const float *)chunk_ptr(a_oc, ch) : (n_oc ? (const float *)(c->dev + o_oc) : nullptr),
                              per_problem_oc ? n : Bo,
@@ -750,9 +806,12 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
                              per_problem_w ? n : Bw, (const int32_t *)chunk_ptr(a_idx, ch),
                              (const float *)chunk_ptr(a_cs, ch), (float *)chunk_ptr(a_plan, ch),
                              (float *)chunk_ptr(a_loss, ch), (int32_t *)chunk_ptr(a_best, ch), nullptr, n, st);
+        if (rc) break;
+        if (cudaEventRecord(c->solved[ch], st) != cudaSuccess ||
+            cudaStreamWaitEvent(s_out, c->solved[ch], 0) != cudaSuccess) { rc = OCD_ECUDA; break; }
         for (HostArray *a : {&a_plan, &a_loss, &a_best})
-            if (rc == OCD_OK) rc = d2h_chunk(c, *a, B, b0, n, cap, ch, st);
-        if (rc == OCD_OK && cudaEventRecord(c->done[ch], st) != cudaSuccess) rc = OCD_ECUDA;
+            if (rc == OCD_OK) rc = d2h_chunk(c, *a, B, b0, n, s_out);
+        if (rc == OCD_OK && cudaEventRecord(c->done[ch], s_out) != cudaSuccess) rc = OCD_ECUDA;
     }
     if (rc) {
         cudaDeviceSynchronize();
@@ -761,8 +820,7 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     }
     for (int ch = 0; ch < nchunks; ++ch) {
         if (cudaEventSynchronize(c->done[ch]) != cudaSuccess) { cudaGetLastError(); return OCD_ECUDA; }
-        const int64_t b0 = (int64_t)ch * cap, n = (b0 + cap <= B) ? cap : B - b0;
-        for (HostArray *a : {&a_plan, &a_loss, &a_best}) unstage_chunk(c, *a, B, b0, n, cap, ch);
+        for (HostArray *a : {&a_plan, &a_loss, &a_best}) unstage_chunk(c, *a, B, start[ch], start[ch + 1] - start[ch]);
     }
     return OCD_OK;
 }
