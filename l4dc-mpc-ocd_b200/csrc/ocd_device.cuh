@@ -561,7 +561,11 @@ struct SmemTraj {
     }
 };
 __host__ __device__ inline int seg_u_stride(int H) { return (2 * H) | 1; }
-__host__ __device__ inline int seg_ck_stride(int H, int SEG) { return (4 * ((H + SEG - 1) / SEG)) | 1; }
+// one checkpoint per segment but the first (which starts at the initial state); never zero floats
+__host__ __device__ inline int seg_ck_stride(int H, int SEG) {
+    const int nseg = (H + SEG - 1) / SEG;
+    return (4 * (nseg > 1 ? nseg - 1 : 1)) | 1;
+}
 
 // Forward half of one iteration: roll the robot out and, at every new state, take the gradient of w.phi.
 // Fills the saved per-step values the reverse sweep needs.  VM as in feature_grad.
@@ -710,13 +714,13 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
     const int H = k.H;
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
     const int nseg = (H + SEG - 1) / SEG;
-    {   // pass 1: dynamics only, checkpoint every segment start (all segments but the last are full)
+    {   // pass 1: dynamics only; the state at the start of segments 1.. is checkpointed (segment 0 starts at
+        // the initial state; all segments but the last are full)
         float x = x0, y = y0, v = v0, th = th0;
         const float *us = u.p;
         float *c = ck;
 #pragma unroll 1
         for (int sg = 0; sg < nseg - 1; ++sg, us += 2 * SEG, c += 4) {
-            c[0] = x; c[1] = y; c[2] = v; c[3] = th;
 #pragma unroll
             for (int i = 0; i < SEG; ++i) {
                 float sn, cs;
@@ -730,20 +734,23 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
                 v = fmaf(total, k.dt, v);
                 th = fmaf(oc, k.dt, th);
             }
+            c[0] = x; c[1] = y; c[2] = v; c[3] = th;
         }
-        c[0] = x; c[1] = y; c[2] = v; c[3] = th;
     }
     float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
     const int ostep = LIN ? 0 : NO * 2 * P;                    // slab floats per horizon step
     float *us = u.p + 2 * SEG * (nseg - 1);
-    const float *c = ck + 4 * (nseg - 1);
+    const float *c = ck + 4 * (nseg - 2);                      // checkpoint of the last segment (sg - 1)
     const float *os = oth + (size_t)SEG * (nseg - 1) * ostep;
     float tbase = (float)(SEG * (nseg - 1));                   // steps before this segment
     int rem = H - SEG * (nseg - 1);                            // steps in this segment (last one may be short)
 #pragma unroll 1
     for (int sg = nseg - 1; sg >= 0; --sg, us -= 2 * SEG, c -= 4, os -= SEG * ostep, rem = SEG, tbase -= (float)SEG) {
-        float x = c[0], y = c[1], v = c[2], th = c[3];
+        float x = x0, y = y0, v = v0, th = th0;
+        if (sg > 0) {
+            x = c[0]; y = c[1]; v = c[2]; th = c[3];
+        }
         float sn, cs;
         Mth<PRECISE>::sincos_(th, sn, cs);
         float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];

@@ -82,7 +82,7 @@ static constexpr int kSeg = 5;    // steps per segment of the runtime-horizon ke
 // lin: the slab holds (x0, dx, y0, dy) per other car instead of a position per horizon step
 // (worth its two extra FFMA per car and step only once the per-step slab would crowd out resident blocks)
 __host__ __device__ inline bool slab_is_linear(bool seg, bool precise, int other_mode, int H, int NO) {
-    return seg && !precise && other_mode == 0 && H * NO >= 100;
+    return seg && !precise && other_mode == 0 && (H * NO >= 100 || H >= 32);
 }
 
 __host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode, bool seg, bool lin) {
