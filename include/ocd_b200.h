@@ -128,6 +128,18 @@ int ocd_reward_grad_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
                           float *reward /*[B]*/, float *grad /*[H][2][B] or NULL*/,
                           int64_t B, void *stream);
 
+/* Jacobian of the horizon-summed features with respect to the controls: what the reference's inverse
+ * optimal control classes take from tf.GradientTape -- segment_loss's d r / d u = J^T w
+ * (interact_drive/reward_design/first_order_ioc.py:62-91) and segment_jacobian / total_jacobian
+ * (:213-268).  Row i is the gradient of sum_t phi_i(s_{t+1}) with TensorFlow's gradient conventions,
+ * i.e. ocd_reward_grad_batch with weights = e_i; other cars as in ocd_reward_grad_batch.
+ * Outputs: phi_sum [K][B], jac [K][H][2][B]. */
+int ocd_feature_jacobian_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
+                               const float *controls /*[H][2][B]*/,
+                               const float *other_controls, int64_t Bo,
+                               float *phi_sum /*[K][B]*/, float *jac /*[K][H][2][B]*/,
+                               int64_t B, void *stream);
+
 /* NaivePlanner.generate_plan (interact_drive/planner/naive_planner.py:81-164) + Keras SGD
  * (call sites :28,:153): S starts x n_iter gradient steps, final loss per start, first-minimum
  * argmin.  cur_speed ([B] or NULL -> world's robot speed) feeds the extra_inits starts (:114-116).

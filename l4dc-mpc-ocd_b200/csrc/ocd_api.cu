@@ -92,6 +92,12 @@ k_reward_grad(const __grid_constant__ KParams k, const float *world, const float
     }
 }
 
+// One-hot weight vectors: row i of an 8x8 identity selects feature i.  ocd_feature_jacobian_batch runs
+// k_reward_grad once per feature with these as the (shared) weights.
+__device__ float g_onehot[(OCD_MAX_LANES + 4) * (OCD_MAX_LANES + 4)] = {
+    1, 0, 0, 0, 0, 0, 0, 0,  0, 1, 0, 0, 0, 0, 0, 0,  0, 0, 1, 0, 0, 0, 0, 0,  0, 0, 0, 1, 0, 0, 0, 0,
+    0, 0, 0, 0, 1, 0, 0, 0,  0, 0, 0, 0, 0, 1, 0, 0,  0, 0, 0, 0, 0, 0, 1, 0,  0, 0, 0, 0, 0, 0, 0, 1};
+
 template <bool PRECISE>
 __global__ void __launch_bounds__(128)
 k_features(const __grid_constant__ KParams k, const float *world, float *phi, long long B) {
@@ -504,6 +510,34 @@ int ocd_reward_grad_batch(const ocd_params *p, const float *world, const float *
     else
         k_reward_grad<false><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo, weights,
                                                                      Bw, weight_idx, reward, grad, B);
+    return cuda_status();
+}
+
+int ocd_feature_jacobian_batch(const ocd_params *p, const float *world, const float *controls,
+                               const float *other_controls, int64_t Bo, float *phi_sum, float *jac, int64_t B,
+                               void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!world || !controls || !phi_sum || !jac || B < 0) return OCD_EINVAL;
+    if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
+    float *eye = nullptr;
+    if (cudaGetSymbolAddress((void **)&eye, g_onehot) != cudaSuccess) {
+        cudaGetLastError();
+        return OCD_ECUDA;
+    }
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    constexpr int KM = OCD_MAX_LANES + 4;
+    for (int i = 0; i < k.K; ++i) {      // row i: the reward with weights e_i is the summed feature i
+        float *r = phi_sum + (size_t)i * B, *g = jac + (size_t)i * k.H * 2 * B;
+        if (p->math_mode == 1)
+            k_reward_grad<true><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo,
+                                                                        eye + i * KM, 1, nullptr, r, g, B);
+        else
+            k_reward_grad<false><<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo,
+                                                                         eye + i * KM, 1, nullptr, r, g, B);
+    }
     return cuda_status();
 }
 

@@ -269,6 +269,28 @@ class Engine:
         self._kernel_launches += 1 if B else 0
         return (R, G.permute(2, 0, 1).contiguous()) if grad else R
 
+    def feature_jacobian(self, p: PlannerParams, world, controls, other_controls=None):
+        """world [B, C, 4]; controls [B, H, 2] -> (phi_sum [B, K], jac [B, K, H, 2]): the horizon-summed
+        features and their Jacobian with respect to the controls (row i = d sum_t phi_i / d u)."""
+        ws = self._world(p, world)
+        B = ws.shape[-1]
+        u = torch.as_tensor(controls, dtype=torch.float32, device=self.device)
+        if u.dim() == 2:
+            u = u.unsqueeze(0)
+        if tuple(u.shape) != (B, p.H, 2):
+            raise ValueError(f"controls must have shape [{B}, {p.H}, 2], got {tuple(u.shape)}")
+        us = u.permute(1, 2, 0).contiguous()
+        oc, Bo = self._other_controls(p, other_controls, B)
+        phi = torch.empty((p.K, B), dtype=torch.float32, device=self.device)
+        jac = torch.empty((p.K, p.H, 2, B), dtype=torch.float32, device=self.device)
+        ps = p.c_struct()
+        with torch.cuda.device(self.device):
+            rc = N.lib.ocd_feature_jacobian_batch(C.addressof(ps), _ptr(ws), _ptr(us), _ptr(oc), Bo, _ptr(phi),
+                                                  _ptr(jac), B, self._stream())
+        N.check(rc, "ocd_feature_jacobian_batch")
+        self._kernel_launches += p.K if B else 0
+        return phi.t().contiguous(), jac.permute(3, 0, 1, 2).contiguous()
+
     def features(self, p: PlannerParams, world) -> torch.Tensor:
         """world [B, C, 4] -> phi [B, K]."""
         ws = self._world(p, world)

@@ -208,3 +208,18 @@ def test_torch_custom_ops_register_and_refuse_cpu():
         assert [tuple(o.shape) for o in out] == [(6, 2, 100), (6, 100), (100,)]
     with pytest.raises(RuntimeError):    # no CPU kernel behind the op
         torch.ops.ocd_b200.solve(torch.zeros((3, 4, 2)), torch.zeros((6, 1)), None, None, T.pack_params(p))
+
+
+def test_first_order_ioc_host_math():
+    """The optimisers of the IOC drop-ins are host computations on the Jacobian the engine returns:
+    the SVD direction and Keras-style Adam on the normalised weights both recover a planted null vector."""
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import first_order_ioc as F
+    rng = np.random.default_rng(0)
+    w = F.l2_normalize(rng.normal(size=7))
+    A = rng.normal(size=(7, 12))
+    A -= np.outer(w, w @ A)                       # every column orthogonal to w  =>  J^T w = 0
+    assert abs(abs(F.nullspace_weights(A) @ w) - 1) < 1e-9
+    theta = F.adam_on_sphere([A[:, :2], A[:, 2:]], np.ones(7), 1.0, 300)
+    assert abs(abs(F.l2_normalize(theta) @ w) - 1) < 1e-6
+    assert F.gradient_norm_loss(w, [A]) < 1e-20 < F.gradient_norm_loss(F.l2_normalize(np.ones(7)), [A])
+    assert abs(np.linalg.norm(F.l2_normalize(np.zeros(3) + 1e-30))) <= 1.0
