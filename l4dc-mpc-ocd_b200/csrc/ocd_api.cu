@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "ocd_kernels.cuh"
 
@@ -719,6 +721,41 @@ static int chunk_schedule(int64_t B, int64_t *start) {
     return m;
 }
 
+// Staging copies between pageable user arrays and the context's pinned area: `rows` row segments of
+// `bytes` bytes each.  One core moves ~10 GB/s, far less than the PCIe link, so copies above 1 MiB are
+// split over a few short-lived threads (by bytes, not by rows: a chunk has as few as one row).
+static void copy_rows(char *dst, size_t dst_stride, const char *src, size_t src_stride, int rows, size_t bytes) {
+    const size_t total = (size_t)rows * bytes;
+    unsigned nt = 1;
+    if (total >= (1u << 20)) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        nt = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+        const unsigned by_size = (unsigned)(total >> 19);          // at least 512 KiB per thread
+        if (nt > by_size) nt = by_size;
+    }
+    auto span = [=](size_t lo, size_t hi) {                         // bytes [lo, hi) of the rows laid end to end
+        while (lo < hi) {
+            const size_t r = lo / bytes, off = lo % bytes;
+            const size_t len = (bytes - off < hi - lo) ? bytes - off : hi - lo;
+            std::memcpy(dst + r * dst_stride + off, src + r * src_stride + off, len);
+            lo += len;
+        }
+    };
+    if (nt <= 1) {
+        span(0, total);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(nt - 1);
+    const size_t per = ((total + nt - 1) / nt + 63) & ~(size_t)63;
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t lo = per * t, hi = lo + per < total ? lo + per : total;
+        if (lo < hi) pool.emplace_back(span, lo, hi);
+    }
+    span(0, per < total ? per : total);
+    for (std::thread &th : pool) th.join();
+}
+
 // One [rows][B] host array moved in column chunks.  Pinned user memory is copied in place (a
 // strided 2-D copy); pageable memory goes through the context's pinned staging area.
 struct HostArray {
@@ -738,8 +775,7 @@ static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
                               cudaMemcpyHostToDevice, st);
     } else {
         char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
-        for (int r = 0; r < a.rows; ++r)
-            std::memcpy(stage + (size_t)r * n * a.elem, a.user + ((size_t)r * B + b0) * a.elem, n * a.elem);
+        copy_rows(stage, n * a.elem, a.user + b0 * a.elem, B * a.elem, a.rows, n * a.elem);
         e = cudaMemcpyAsync(dst, stage, (size_t)a.rows * n * a.elem, cudaMemcpyHostToDevice, st);
     }
     return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
@@ -760,8 +796,7 @@ static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
 static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n) {
     if (a.pinned) return;
     const char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
-    for (int r = 0; r < a.rows; ++r)
-        std::memcpy(a.user + ((size_t)r * B + b0) * a.elem, stage + (size_t)r * n * a.elem, n * a.elem);
+    copy_rows(a.user + b0 * a.elem, B * a.elem, stage, n * a.elem, a.rows, n * a.elem);
 }
 
 // The batch is cut into column chunks that flow through four streams linked by per-chunk events: one
@@ -810,7 +845,7 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     const size_t o_w = dev.take(n_w), s_w = pin.take(pin_w ? 0 : n_w);
     const size_t o_oc = dev.take(n_oc), s_oc = pin.take(pin_oc ? 0 : n_oc);
     if ((rc = ctx_reserve(c, dev.off, pin.off))) return rc;
-    if (n_w && !pin_w) std::memcpy(c->pin + s_w, weights, n_w);
+    if (n_w && !pin_w) copy_rows(c->pin + s_w, n_w, (const char *)weights, n_w, 1, n_w);
     if (n_oc && !pin_oc) std::memcpy(c->pin + s_oc, other_controls, n_oc);
     cudaStream_t s0 = c->lanes[0];        // the H2D stream: chunk copies are ordered behind the shared inputs
     if (n_w && cudaMemcpyAsync(c->dev + o_w, pin_w ? (const char *)weights : c->pin + s_w, n_w, cudaMemcpyHostToDevice,

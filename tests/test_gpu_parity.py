@@ -393,6 +393,21 @@ def test_host_api_matches_device_api(engine):
     d = engine.episodes(_pp(spec.params, 0), _sc(spec.scenario), ri, w, w, 5)["returns"].cpu().numpy()
     h = ctx.episodes_soa(_pp(spec.params, 0), _sc(spec.scenario), np.ascontiguousarray(ri.T), w[:, None], w, 5)
     np.testing.assert_array_equal(h, d)
+    # a batch large enough for the chunk pipeline and the multi-threaded staging copies: pageable arrays,
+    # pinned arrays and the device API must agree bit for bit (per-problem weights travel with the chunks)
+    B = 300000 + 17
+    batch = synthetic.make_batch(B, seed=10)
+    w_full = np.ascontiguousarray(batch["weights"][batch["weight_idx"]].T)
+    world_soa = np.ascontiguousarray(batch["world"].transpose(1, 2, 0))
+    dev = engine.solve(p, batch["world"], batch["weights"][batch["weight_idx"]])
+    pageable = ctx.solve_soa(p, world_soa, w_full)
+    pw, pwt = ocd.HostContext.pinned_empty(world_soa.shape), ocd.HostContext.pinned_empty(w_full.shape)
+    pw[...], pwt[...] = world_soa, w_full
+    pinned = ctx.solve_soa(p, pw, pwt)
+    for got in (pageable, pinned):
+        np.testing.assert_array_equal(got["plan"].transpose(2, 0, 1), dev["plan"].cpu().numpy())
+        np.testing.assert_array_equal(got["losses"].T, dev["losses"].cpu().numpy())
+        np.testing.assert_array_equal(got["best"], dev["best"].cpu().numpy())
     ctx.close()
 
 
@@ -436,6 +451,23 @@ def test_full_size_properties(engine):
     same = ref["best"] == a["best"].cpu().numpy()[sel]
     assert same.mean() > 0.9
     assert np.max(np.abs(got[same] - ref["plan"][same])) <= 1e-3
+
+
+def test_latency_variant_matches_throughput_kernel(engine):
+    """Batches of at most ~12 600 problems run the latency variant of the kernel (straight-line forward
+    sweep, no votes), larger ones the throughput kernel: the same problems must get the same answer either
+    way.  Also covers the replanning shape (two other cars, two lanes)."""
+    for C, lane_x, ts in ((2, (-0.1, 0.0, 0.1), 1.0), (3, (-0.05, 0.05), 1.2)):
+        B, n = 65536, 4096
+        batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
+        p = ocd.PlannerParams(C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts)
+        big = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"])
+        small = engine.solve(p, batch["world"][:n], batch["weights"], weight_idx=batch["weight_idx"][:n])
+        same = (big["plan"][:n] == small["plan"]).all(dim=2).all(dim=1)
+        assert same.float().mean().item() >= 0.999, same.float().mean().item()
+        assert torch.equal(big["best"][:n][same], small["best"][same])
+        close = (big["plan"][:n] - small["plan"]).abs().amax(dim=(1, 2)) <= 1e-3
+        assert close.float().mean().item() >= 0.995
 
 
 # ---- edge shapes: limits of the ABI, ragged batches, every weight / control sharing mode -----------------
