@@ -309,7 +309,11 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x, bool
 // VM = 1 (FAST only): no warp votes and no rare-path branches -- every block below is computed
 // unconditionally (the clamped formulations make that safe), so the whole horizon is one basic block the
 // scheduler can interleave; whatever needs an exact rule (lane tie, collision tie) raises `flag` instead.
-template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0>
+// RAWG (time-parallel kernels): return the FACTORS of three of the gradient components instead of the
+// products -- gv := ke (d/dv = ke sin th), gth := unused, gy := hy (d/dy = wcy hy) -- because the consumer
+// there sits behind a warp shuffle and must form the same fused multiply-adds (ke*sn + lv, ...) that the
+// compiler contracts in the single-thread kernels, or the two kernel families would round differently.
+template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0, bool RAWG = false>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
                                              float &gx, float &gy, float &gv, float &gth, float tf, bool &flag) {
@@ -318,8 +322,8 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
     {
         const float e = fmaf(v, sn, -k.ts);
         const float ke = (e * e <= k.bound) ? (w.w0x2 * e) : 0.0f;
-        gv = ke * sn;
-        gth = (ke * v) * cs;
+        gv = RAWG ? ke : ke * sn;
+        gth = RAWG ? 0.0f : (ke * v) * cs;
     }
     // lanes: sum_i w_i 10 (x - l_i)^2 and the min over lanes                 merging.py:61-65
     gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE, VM>(k, x, flag), fmaf(w.GA, x, w.GB));
@@ -449,7 +453,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
             }
         }
         gx = fmaf(w.wcx, hx, gx);
-        gy = w.wcy * hy;
+        gy = RAWG ? hy : w.wcy * hy;
     }
     // fence                                                                    merging.py:80-81
     {
@@ -695,6 +699,104 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
     for (int it = 0; it < k.n_iter; ++it)
         sgd_iteration<HT, NOT_, LT, PRECISE, true, LAT>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, nullptr, nullptr);
     return -rollout_reward<HT, LT, PRECISE, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Time-parallel solve: the lowest-latency path, for batches so small that even the latency variant
+// leaves the GPU idle (the reference's real configurations: 45-180 episodes).  kTG = 8 consecutive
+// lanes share one (problem, start); lane t owns horizon step t (HT <= kTG; spare lanes shadow the
+// last step).  Per iteration the lanes all-gather the controls (2 HT shuffles), every lane rolls the
+// cheap dynamics for the whole horizon, evaluates the expensive feature gradient for ITS step only,
+// the gradients are all-gathered (4 HT shuffles) and every lane runs the short reverse sweep, keeping the
+// update of its own control.  Same formulas in the same order as sgd_iteration, so the result is bit
+// for bit the one of the other kernels; the dependent chain per iteration shrinks from H feature
+// evaluations to one.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTG = 8;
+
+template <int HT, int NOT_, int LT>
+__device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w, const float *wraw, int ws,
+                                                float x0, float y0, float v0, float th0, const float *oth, int P,
+                                                int t, float a_init, float w_init, Traj<HT> &u) {
+    static_assert(HT > 0 && HT <= kTG, "time-parallel solve: one lane per horizon step");
+    constexpr int NO = NOT_;
+    const int tt = t < HT ? t : HT - 1;
+    float ua = a_init, uw = w_init;                      // this lane's control: step tt
+    float sn0, cs0;
+    Mth<false>::sincos_(th0, sn0, cs0);
+    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    const float lra = k.lr * k.hdt2, lrv = k.lr * k.dt;
+    const float *omine = oth + (size_t)tt * NO * 2 * P;
+#pragma unroll 1
+    for (int it = 0; it < k.n_iter; ++it) {
+        float A[HT], W[HT], sv[HT + 1], sc[HT + 1], ss[HT + 1], sd[HT];    // [j]: at the state before step j
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            A[j] = __shfl_sync(OCD_FULL, ua, j, kTG);
+            W[j] = __shfl_sync(OCD_FULL, uw, j, kTG);
+        }
+        float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
+        float mx_ = 0.0f, my_ = 0.0f, mv_ = 0.0f, msn = 0.0f, mcs = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            const float ac = fmaxf(fminf(A[j], 4.0f), -8.0f);
+            const float oc = fmaxf(fminf(W[j], 4.0f), -4.0f);
+            const float total = fmaf(-k.mu, v * v, ac);
+            const float dist = fmaf(total, k.hdt2, v * k.dt);
+            sv[j] = v; sc[j] = cs; ss[j] = sn; sd[j] = dist;
+            x = fmaf(cs, dist, x);
+            y = fmaf(sn, dist, y);
+            v = fmaf(total, k.dt, v);
+            th = fmaf(oc, k.dt, th);
+            Mth<false>::sincos_(th, sn, cs);
+            const bool mine = j == tt;
+            mx_ = mine ? x : mx_; my_ = mine ? y : my_; mv_ = mine ? v : mv_;
+            msn = mine ? sn : msn; mcs = mine ? cs : mcs;
+        }
+        sv[HT] = v; sc[HT] = cs; ss[HT] = sn;
+        float gx, hy, ke, unused;
+        bool flag = false;
+        feature_grad<NOT_, LT, false, false, 1, true>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke, unused,
+                                                      0.0f, flag);
+        if (__any_sync(OCD_FULL, flag))                  // rare: a lane needs an exact tie rule
+            feature_grad<NOT_, LT, false, false, 0, true>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke,
+                                                          unused, 0.0f, flag);
+        float GX[HT], HY[HT], KE[HT];
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            GX[j] = __shfl_sync(OCD_FULL, gx, j, kTG);
+            HY[j] = __shfl_sync(OCD_FULL, hy, j, kTG);
+            KE[j] = __shfl_sync(OCD_FULL, ke, j, kTG);
+        }
+        float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < HT; ++jj) {
+            const int j = HT - 1 - jj;
+            // the gradient at s_{j+1} plus the adjoint, fused exactly as the single-thread kernels fuse them
+            const float mx = GX[j] + lx;
+            const float my = fmaf(w.wcy, HY[j], ly);
+            const float mv = fmaf(KE[j], ss[j + 1], lv);
+            const float mth = fmaf(__fmul_rn(KE[j], sv[j + 1]), sc[j + 1], lth);
+            const float ld = fmaf(sc[j], mx, ss[j] * my);
+            const float a = A[j], om = W[j];
+            const bool in_a = (a >= -8.0f) && (a <= 4.0f);
+            const bool in_w = fabsf(om) <= 4.0f;
+            lv = fmaf(fmaf(c1, sv[j], 1.0f), mv, fmaf(c2, sv[j], k.dt) * ld);
+            lth = fmaf(sd[j], fmaf(sc[j], my, -(ss[j] * mx)), mth);
+            lx = mx;
+            ly = my;
+            const float na = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
+            const float nw = in_w ? fmaf(lrv, mth, om) : om;
+            ua = (j == tt) ? na : ua;
+            uw = (j == tt) ? nw : uw;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < HT; ++j) {
+        u.ua[j] = __shfl_sync(OCD_FULL, ua, j, kTG);
+        u.uw[j] = __shfl_sync(OCD_FULL, uw, j, kTG);
+    }
+    return -rollout_reward<HT, LT, false, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -357,6 +357,195 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Time-parallel variants (solve_start_tp): kTG = 8 lanes per (problem, start), kTP = 4 problems per
+// block, thread = ((s * kTP + p) * kTG + t): warp s still runs start s, of 4 problems x 8 step-lanes.
+// Everything but the solve itself is k_solve / k_episode with the per-problem work on lane t == 0.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTP = 4;
+
+__device__ __forceinline__ void tp_start_controls(const KParams &k, int s, float cur_speed, float &a0, float &w0) {
+    a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(cur_speed, cur_speed)) : 0.0f;      // naive_planner.py:107-118
+    const int m = s % 3;
+    w0 = (m == 0) ? 0.0f : ((m == 1) ? -k.turn : k.turn);
+}
+
+template <int HT, int NOT_, int LT>
+__global__ void __launch_bounds__(6 * kTP * kTG, 1) k_solve_tp(const __grid_constant__ KParams k, const SolveArgs a) {
+    extern __shared__ float smem_raw[];
+    constexpr int P = kTP;
+    const Smem m = carve(smem_raw, k, P, false, false, false);
+    const int t = threadIdx.x % kTG, g = threadIdx.x / kTG, p = g % P, s = g / P;
+    const long long b_raw = (long long)blockIdx.x * P + p;
+    const bool live = b_raw < a.B;
+    const long long b = live ? b_raw : a.B - 1;
+    const long long B = a.B;
+    if (s == 0 && t == 0) {
+        const long long wc = weight_column(a.weight_idx, a.Bw, b);
+        for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.weights[(size_t)i * a.Bw + wc];
+        for (int j = 0; j < k.NO; ++j) {
+            const float *st = a.world + (size_t)(j + 1) * 4 * B + b;
+            const float *oc = nullptr;
+            long long ocs = 0;
+            if (k.other_mode == 1) {
+                ocs = a.Bo;
+                oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
+            }
+            predict_other<false>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P, false);
+        }
+    }
+    __syncthreads();
+    const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
+    const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
+    float a0, w0;
+    tp_start_controls(k, s, a.cur_speed ? a.cur_speed[b] : v0, a0, w0);
+    Traj<HT> u;
+    const float loss = solve_start_tp<HT, NOT_, LT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, t, a0, w0, u);
+    if (t == 0) {
+        m.loss[s * P + p] = loss;
+        if (live) {
+            a.losses[(size_t)s * B + b] = loss;
+            if (a.all_plans) {
+#pragma unroll
+                for (int j = 0; j < HT; ++j) {
+                    a.all_plans[((size_t)(s * HT + j) * 2 + 0) * B + b] = u.ua[j];
+                    a.all_plans[((size_t)(s * HT + j) * 2 + 1) * B + b] = u.uw[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int bi = 0;
+    float bl = m.loss[p];
+    for (int q = 1; q < k.S; ++q) {
+        const float l = m.loss[q * P + p];
+        if (l < bl) { bl = l; bi = q; }
+    }
+    if (live && s == bi && t == 0) {
+        a.best[b] = bi;
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            a.plan[(size_t)(j * 2 + 0) * B + b] = u.ua[j];
+            a.plan[(size_t)(j * 2 + 1) * B + b] = u.uw[j];
+        }
+    }
+}
+
+template <int HT, int NOT_, int LT>
+__global__ void __launch_bounds__(6 * kTP * kTG, 1)
+k_episode_tp(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
+    extern __shared__ float smem_raw[];
+    constexpr int P = kTP;
+    const Smem m = carve(smem_raw, k, P, true, false, false);
+    const int t = threadIdx.x % kTG, g = threadIdx.x / kTG, p = g % P, s = g / P;
+    const bool lead = s == 0 && t == 0;                  // the thread that owns problem p's world
+    const long long b_raw = (long long)blockIdx.x * P + p;
+    const bool live = b_raw < a.B;
+    const long long b = live ? b_raw : a.B - 1;
+    const long long B = a.B;
+    const int C = k.NO + 1;
+
+    if (threadIdx.x < k.K) m.wtrue[threadIdx.x] = a.true_weights[threadIdx.x];
+    int unlucky = 0;
+    if (lead) {
+        const long long wc = weight_column(a.weight_idx, a.Bw, b);
+        for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.plan_weights[(size_t)i * a.Bw + wc];
+        for (int c = 0; c < 4; ++c) m.world[c * P + p] = a.robot_init[(size_t)c * B + b];
+        for (int j = 0; j < k.NO; ++j)
+            for (int c = 0; c < 4; ++c)
+                m.world[((j + 1) * 4 + c) * P + p] =
+                    a.other_init ? a.other_init[(size_t)(j * 4 + c) * B + b] : sc.init_state[j][c];
+        if (a.unlucky_idx) unlucky = a.unlucky_idx[b];
+    }
+    __syncthreads();
+    const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
+    float ret = 0.0f;
+
+    for (int i = 0; i < a.T; ++i) {
+        const int ti = a.t0 + i;
+        if (lead) {
+            if (sc.critical_t > 0 && ti + 1 == sc.critical_t && unlucky >= 1 && unlucky < C)
+                for (int c = 0; c < 4; ++c) m.world[(unlucky * 4 + c) * P + p] = sc.teleport_state[c];
+            if (a.traj_states && live)
+                for (int c = 0; c < C * 4; ++c)
+                    a.traj_states[((size_t)i * C * 4 + c) * B + b] = m.world[c * P + p];
+            {
+                const float x = m.world[p], y = m.world[P + p], v = m.world[2 * P + p], th = m.world[3 * P + p];
+                float sn, cs;
+                Mth<false>::sincos_(th, sn, cs);
+                ret = __fadd_rn(ret, reward_value<LT, false, false>(k, m.wtrue, 1, x, y, v, sn, m.world + 4 * P + p,
+                                                                    4 * P, P));
+            }
+            for (int j = 0; j < k.NO; ++j) {
+                const float *w = m.world + (size_t)(j + 1) * 4 * P + p;
+                float x = w[0], y = w[P], v = w[2 * P], th = w[3 * P];
+                for (int tq = 0; tq < k.H; ++tq) {
+                    float oa = 0.0f, oo = 0.0f;
+                    if (k.other_mode == 1 && sc.kind[j] == 1) {   // plan replayed from index 0 (quirk Q4)
+                        const bool in_plan = tq < sc.plan_len[j];
+                        oa = in_plan ? sc.plan[j][tq][0] : sc.control[j][0];
+                        oo = in_plan ? sc.plan[j][tq][1] : sc.control[j][1];
+                    }
+                    other_model_step<false>(x, y, v, th, k.other_mode == 1, oa, oo, k.dt, k.dt2);
+                    m.oth[(size_t)((tq * k.NO + j) * 2 + 0) * P + p] = slab_x<false>(x);
+                    m.oth[(size_t)((tq * k.NO + j) * 2 + 1) * P + p] = slab_y<false>(y);
+                }
+            }
+        }
+        __syncthreads();
+
+        const float x0 = m.world[p], y0 = m.world[P + p], v0 = m.world[2 * P + p], th0 = m.world[3 * P + p];
+        float a0, w0;
+        tp_start_controls(k, s, v0, a0, w0);
+        Traj<HT> u;
+        const float loss = solve_start_tp<HT, NOT_, LT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, t, a0, w0,
+                                                        u);
+        if (t == 0) {
+            m.loss[s * P + p] = loss;
+            m.u0[(s * 2 + 0) * P + p] = u.ua[0];
+            m.u0[(s * 2 + 1) * P + p] = u.uw[0];
+        }
+        __syncthreads();
+
+        if (lead) {
+            int bi = 0;
+            float bl = m.loss[p];
+            for (int q = 1; q < k.S; ++q) {
+                const float l = m.loss[q * P + p];
+                if (l < bl) { bl = l; bi = q; }
+            }
+            const float ua = m.u0[(bi * 2 + 0) * P + p], uw = m.u0[(bi * 2 + 1) * P + p];
+            if (live) {
+                if (a.traj_controls) {
+                    a.traj_controls[((size_t)i * 2 + 0) * B + b] = ua;
+                    a.traj_controls[((size_t)i * 2 + 1) * B + b] = uw;
+                }
+                if (a.traj_best) a.traj_best[(size_t)i * B + b] = bi;
+            }
+            {
+                float x = x0, y = y0, v = v0, th = th0;
+                dynamics_step<false>(x, y, v, th, ua, uw, k.dt, k.dt2, k.mu);
+                m.world[p] = x; m.world[P + p] = y; m.world[2 * P + p] = v; m.world[3 * P + p] = th;
+            }
+            for (int j = 0; j < k.NO; ++j) {
+                float *w = m.world + (size_t)(j + 1) * 4 * P + p;
+                float x = w[0], y = w[P], v = w[2 * P], th = w[3 * P];
+                const bool in_plan = sc.kind[j] == 1 && ti < sc.plan_len[j];   // fixed_plan_car.py:25-31
+                const float oa = in_plan ? sc.plan[j][ti][0] : sc.control[j][0];
+                const float oo = in_plan ? sc.plan[j][ti][1] : sc.control[j][1];
+                dynamics_step<false>(x, y, v, th, oa, oo, k.dt, k.dt2, sc.friction[j]);
+                w[0] = x; w[P] = y; w[2 * P] = v; w[3 * P] = th;
+            }
+        }
+        __syncthreads();
+    }
+    if (lead && live) {
+        a.returns[b] = ret;
+        if (a.final_world)
+            for (int c = 0; c < C * 4; ++c) a.final_world[(size_t)c * B + b] = m.world[c * P + p];
+    }
+}
+
 inline int cuda_status() { return cudaGetLastError() == cudaSuccess ? OCD_OK : OCD_ECUDA; }
 
 template <typename KernelT>
@@ -372,12 +561,21 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
 // A batch is "small" when its warps cannot hide each other's latency: at most two per SM sub-partition
 // of a 148-SM part.  The compile-time-horizon FAST kernels then run their latency variant.
 inline bool small_batch(long long B, int P, int S) { return ((B + P - 1) / P) * S <= 2 * 4 * 148; }
+// ... and "tiny" when the same holds with eight lanes per (problem, start): the time-parallel kernels.
+inline bool tiny_batch(long long B, int S) { return ((B + kTP - 1) / kTP) * S <= 2 * 4 * 148; }
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
+    if constexpr (HAS_LAT && HT <= kTG) {
+        if (tiny_batch(a.B, k.S)) {
+            const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, false, false, false) * sizeof(float);
+            k_solve_tp<HT, NOT_, LT><<<(unsigned)((a.B + kTP - 1) / kTP), k.S * kTP * kTG, tb, st>>>(k, a);
+            return cuda_status();
+        }
+    }
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
     if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT>;
     int rc = prepare_smem(kern, bytes);
@@ -392,6 +590,13 @@ int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
+    if constexpr (HAS_LAT && HT <= kTG) {
+        if (tiny_batch(a.B, k.S)) {
+            const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, true, false, false) * sizeof(float);
+            k_episode_tp<HT, NOT_, LT><<<(unsigned)((a.B + kTP - 1) / kTP), k.S * kTP * kTG, tb, st>>>(k, sc, a);
+            return cuda_status();
+        }
+    }
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
     if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT>;
     int rc = prepare_smem(kern, bytes);

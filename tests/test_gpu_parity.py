@@ -453,21 +453,28 @@ def test_full_size_properties(engine):
     assert np.max(np.abs(got[same] - ref["plan"][same])) <= 1e-3
 
 
-def test_latency_variant_matches_throughput_kernel(engine):
-    """Batches of at most ~12 600 problems run the latency variant of the kernel (straight-line forward
-    sweep, no votes), larger ones the throughput kernel: the same problems must get the same answer either
-    way.  Also covers the replanning shape (two other cars, two lanes)."""
-    for C, lane_x, ts in ((2, (-0.1, 0.0, 0.1), 1.0), (3, (-0.05, 0.05), 1.2)):
-        B, n = 65536, 4096
+def test_latency_variants_match_throughput_kernel(engine):
+    """Up to ~1 500 problems run the time-parallel kernel (8 lanes per start), up to ~12 600 the latency
+    variant (straight-line forward sweep, no votes), larger batches the throughput kernel: the same
+    problems must get the same answer whichever runs.  Covers the finite_horizon shape, the replanning shape
+    (two other cars, two lanes), H=6 and the six-start set."""
+    stats, ok = [], True
+    for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
+                                    (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True)):
+        B = 32768 if extra else 65536
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
-        p = ocd.PlannerParams(C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts)
-        big = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"])
-        small = engine.solve(p, batch["world"][:n], batch["weights"], weight_idx=batch["weight_idx"][:n])
-        same = (big["plan"][:n] == small["plan"]).all(dim=2).all(dim=1)
-        assert same.float().mean().item() >= 0.999, same.float().mean().item()
-        assert torch.equal(big["best"][:n][same], small["best"][same])
-        close = (big["plan"][:n] - small["plan"]).abs().amax(dim=(1, 2)) <= 1e-3
-        assert close.float().mean().item() >= 0.995
+        p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra)
+        big = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"], all_plans=True)
+        for n in (4096, 500):
+            small = engine.solve(p, batch["world"][:n], batch["weights"], weight_idx=batch["weight_idx"][:n],
+                                 all_plans=True)
+            same = (big["all_plans"][:n] == small["all_plans"]).flatten(1).all(dim=1)
+            close = (big["plan"][:n] - small["plan"]).abs().amax(dim=(1, 2)) <= 1e-3
+            stats.append((C, H, extra, n, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
+            ok = ok and same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
+            ok = ok and torch.equal(big["best"][:n][same], small["best"][same])
+            ok = ok and torch.equal(big["losses"][:n][same], small["losses"][same])
+    assert ok, stats
 
 
 # ---- edge shapes: limits of the ABI, ragged batches, every weight / control sharing mode -----------------
