@@ -745,14 +745,20 @@ static void copy_rows(char *dst, size_t dst_stride, const char *src, size_t src_
         span(0, total);
         return;
     }
-    std::vector<std::thread> pool;
-    pool.reserve(nt - 1);
     const size_t per = ((total + nt - 1) / nt + 63) & ~(size_t)63;
-    for (unsigned t = 1; t < nt; ++t) {
-        const size_t lo = per * t, hi = lo + per < total ? lo + per : total;
-        if (lo < hi) pool.emplace_back(span, lo, hi);
+    std::vector<std::thread> pool;
+    size_t handed = per < total ? per : total;             // bytes [0, handed) are this thread's share
+    try {                                                   // nothing may throw across the C ABI: whatever
+        pool.reserve(nt - 1);                               // could not be handed to a thread is copied here
+        for (unsigned t = 1; t < nt && handed < total; ++t) {
+            const size_t lo = handed, hi = lo + per < total ? lo + per : total;
+            pool.emplace_back(span, lo, hi);
+            handed = hi;
+        }
+    } catch (...) {
     }
     span(0, per < total ? per : total);
+    if (handed < total) span(handed, total);
     for (std::thread &th : pool) th.join();
 }
 

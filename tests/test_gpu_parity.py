@@ -375,6 +375,52 @@ def test_episode_single_step_is_world_step(engine):
     assert abs(total - float(full["returns"][0])) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["finite_horizon", "replanning"])
+def test_episode_full_size_properties(engine, name):
+    """65 536 episodes (the throughput form of the episode kernel; the golden episodes run the time-parallel
+    form): an episode of 6 control steps == two chained launches of 3, permuting the batch permutes the
+    results, weight_idx indirection == expanded weights, the first 500 / 4 000 episodes alone (time-parallel /
+    latency form) give the same returns, and 32 spot checks against the oracle."""
+    B, T = 65536, 6
+    spec = O.scenario_params(name)
+    p, sc = _pp(spec.params, ocd.MATH_FAST), _sc(spec.scenario)
+    rng = np.random.default_rng(12)
+    ri = np.tile(spec.example_init.astype(np.float32), (B, 1))
+    ri[:, 0] += rng.uniform(-0.04, 0.04, B).astype(np.float32)
+    ri[:, 1] += rng.uniform(-0.05, 0.05, B).astype(np.float32)
+    ri[:, 2] += rng.uniform(-0.1, 0.1, B).astype(np.float32)
+    wt = (spec.designer_weights / np.linalg.norm(spec.designer_weights)).astype(np.float32)
+    cand = wt[None] + 0.05 * rng.normal(size=(B // 8, p.K)).astype(np.float32)
+    cand /= np.linalg.norm(cand, axis=1, keepdims=True)
+    widx = (np.arange(B) // 8).astype(np.int32)
+    ul = rng.integers(1, p.C, B).astype(np.int32) if name == "replanning" else None
+    full = engine.episodes(p, sc, ri, cand, wt, T, weight_idx=widx, unlucky_idx=ul, trace=True, final_world=True)
+    # composition
+    a = engine.episodes(p, sc, ri, cand, wt, 3, weight_idx=widx, unlucky_idx=ul, final_world=True)
+    b = engine.episodes(p, sc, a["final_world"][:, 0], cand, wt, 3, weight_idx=widx, unlucky_idx=ul, t0=3,
+                        other_init=a["final_world"][:, 1:], final_world=True)
+    assert torch.equal(b["final_world"], full["final_world"])
+    assert (a["returns"] + b["returns"] - full["returns"]).abs().max().item() <= 1e-5
+    # permutation, weight_idx vs expanded weights
+    perm = rng.permutation(B)
+    c = engine.episodes(p, sc, ri[perm], cand[widx[perm]], wt, T, unlucky_idx=None if ul is None else ul[perm])
+    assert torch.equal(c["returns"], full["returns"][torch.as_tensor(perm, device=full["returns"].device)])
+    # the three kernel forms agree
+    for n in (500, 4000):
+        small = engine.episodes(p, sc, ri[:n], cand, wt, T, weight_idx=widx[:n], unlucky_idx=None if ul is None else ul[:n])
+        same = small["returns"] == full["returns"][:n]
+        assert same.float().mean().item() >= 0.995, (n, same.float().mean().item())
+        assert ((small["returns"] - full["returns"][:n]).abs() <= 1e-3 * full["returns"][:n].abs().clamp(min=1e-3)) \
+            .float().mean().item() >= 0.99
+    # oracle spot checks
+    sel = np.linspace(0, B - 1, 32).astype(np.int64)
+    got = full["returns"].cpu().numpy()[sel]
+    ref = np.array([O.episode(spec.params, spec.scenario, ri[i], cand[widx[i]], wt, T,
+                              unlucky_idx=0 if ul is None else int(ul[i]))["ret"] for i in sel])
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+    assert np.mean(rel <= 1e-3) >= 0.9, rel
+
+
 # ---- host-buffer C ABI ---------------------------------------------------------------------------
 def test_host_api_matches_device_api(engine):
     B = 1000
