@@ -371,7 +371,10 @@ static int digest(const ocd_params *p, KParams &k) {
                 const float t = sorted[j]; sorted[j] = sorted[j - 1]; sorted[j - 1] = t;
             }
         for (int i = 0; i + 1 < p->L; ++i) k.lane_mid[i] = (float)(((double)sorted[i] + (double)sorted[i + 1]) * 0.5);
+        for (int i = 0; i < OCD_MAX_LANES; ++i) k.lane_sorted[i] = i < p->L ? sorted[i] : 0.0f;
     }
+    k.fs_lo = k.fshape * k.thr_lo;
+    k.fs_w = k.fshape * k.thr_w;
     return OCD_OK;
 }
 

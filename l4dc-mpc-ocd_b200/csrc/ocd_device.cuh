@@ -41,6 +41,8 @@ struct KParams {
     float turn;                   // 5*0.13 start angular velocity
     float lane_x[OCD_MAX_LANES];
     float lane_mid[OCD_MAX_LANES];  // midpoints between lanes adjacent in sorted order: where the lane-min ties
+    float lane_sorted[OCD_MAX_LANES];   // lane positions in ascending order
+    float fs_lo, fs_w;            // fence ramp in shape-scaled units: fshape*thr_lo, fshape*thr_w
 };
 
 // collision bump half-widths (merging.py:70-73) and their reciprocals
@@ -208,8 +210,11 @@ __device__ __forceinline__ void fence_vg(const KParams &k, float x, float &f, fl
 // Per-problem weights, pre-combined for the gradient:
 //   sum_i w_i * d/dx[10 (x-l_i)^2] = GA*x + GB ;  w0x2 = 2 w_speed ; wmin20 = 20 w_min ;
 //   wcx / wcy = collision weight times the bump's d n / d position and the -2 of bump'.
+//   compile-time lane count: the nearest lane l* enters d/dx as wmin20 (x - l*), so with GAm = GA + wmin20
+//   and one constant per lane GBl[i] = GB - wmin20 l_i (sorted order) the whole lane term is GAm x + GBl[*].
 struct GradW {
     float w0x2, GA, GB, wmin20, wcol, wfence, wcx, wcy;
+    float GAm, GBl[OCD_MAX_LANES];
 };
 
 template <int LT>
@@ -232,6 +237,14 @@ __device__ __forceinline__ GradW make_gradw(const KParams &k, const float *w /*[
     g.wfence = w[(3 + L) * ws];
     g.wcx = g.wcol * (-2.0f * OCD_BUMP_IX);
     g.wcy = g.wcol * (-2.0f * OCD_BUMP_IY);
+    g.GAm = g.GA + g.wmin20;
+#pragma unroll
+    for (int i = 0; i < OCD_MAX_LANES; ++i) g.GBl[i] = (i < L) ? fmaf(-g.wmin20, k.lane_sorted[i], g.GB) : 0.0f;
+    if (LT > 0) {
+        asm volatile("" : "+f"(g.GAm), "+f"(g.GBl[0]), "+f"(g.GBl[1]));
+        if (LT > 2) asm volatile("" : "+f"(g.GBl[2]));
+        if (LT > 3) asm volatile("" : "+f"(g.GBl[3]));
+    }
     // keep the combined constants in registers: without the barrier ptxas rematerialises GA/GB from
     // the raw weights inside the hot loop (4 extra instructions per horizon step)
     asm volatile("" : "+f"(g.GA), "+f"(g.GB), "+f"(g.wmin20), "+f"(g.w0x2));
@@ -313,7 +326,9 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x, bool
 // products -- gv := ke (d/dv = ke sin th), gth := unused, gy := hy (d/dy = wcy hy) -- because the consumer
 // there sits behind a warp shuffle and must form the same fused multiply-adds (ke*sn + lv, ...) that the
 // compiler contracts in the single-thread kernels, or the two kernel families would round differently.
-template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0, bool RAWG = false>
+// FOLD: use the per-lane folded constants of GradW for the lane term (the register-resident kernels; the
+// segmented kernels are short of registers and keep the three-instruction form).
+template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0, bool RAWG = false, bool FOLD = !LIN>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
                                              float &gx, float &gy, float &gv, float &gth, float tf, bool &flag) {
@@ -326,7 +341,28 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         gth = RAWG ? 0.0f : (ke * v) * cs;
     }
     // lanes: sum_i w_i 10 (x - l_i)^2 and the min over lanes                 merging.py:61-65
-    gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE, VM>(k, x, flag), fmaf(w.GA, x, w.GB));
+    if (LT > 0 && !PRECISE && FOLD) {
+        // nearest lane by the midpoints of the sorted lanes (ascending: the last one passed wins); exact ties
+        // of the feature values are only possible within rounding of a midpoint -- then (warp vote, or the
+        // caller's redo in vote mode 1) the exact rule runs
+        float gb = w.GBl[0], near = 1.0f;
+#pragma unroll
+        for (int i = 1; i < LT; ++i) {
+            const float d = x - k.lane_mid[i - 1];
+            gb = (d > 0.0f) ? w.GBl[i] : gb;
+            near = fminf(near, fabsf(d));
+        }
+        gx = fmaf(w.GAm, x, gb);
+        const bool close = near < 1e-6f;
+        if (VM == 1) {
+            flag = flag || close;
+        } else if (__any_sync(OCD_FULL, close)) {
+            const float exact = fmaf(w.wmin20, lane_min_offset_exact<LT>(k, x), fmaf(w.GA, x, w.GB));
+            gx = close ? exact : gx;
+        }
+    } else {
+        gx = fmaf(w.wmin20, lane_min_offset<LT, PRECISE, VM>(k, x, flag), fmaf(w.GA, x, w.GB));
+    }
     // collision: max_j bump_x * bump_y                                        merging.py:67-78
     if (PRECISE) {
         float best = 0.0f, sx = 0.0f, sy = 0.0f, cnt = 1.0f;
@@ -458,20 +494,20 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
     // fence                                                                    merging.py:80-81
     {
         const float ax = fabsf(x);
-        const float q = ax - k.thr_lo;
         if (PRECISE) {
+            const float q = ax - k.thr_lo;
             if (q > 0.0f) {
                 float f, df;
                 fence_inside<true>(k, x, ax, q, f, df);
                 gx = fmaf(w.wfence, df, gx);
             }
-        } else if (VM == 1 || __any_sync(OCD_FULL, q > 0.0f)) {
-            // T = F1/(F1+F2) = 1/(1 + exp(r1 - r2)), r1 = 1/(shape q), r2 = 1/(shape (width - q));
-            // dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping q and width-q to a tiny positive number
-            // makes the exponential saturate: T = 0, dT = 0 below the ramp and T = 1, dT = 0 above it,
-            // so the three regions need no branch.
-            const float r1 = Mth<false>::rcp_(k.fshape * fmaxf(q, 1e-9f));
-            const float r2 = Mth<false>::rcp_(k.fshape * fmaxf(k.thr_w - q, 1e-9f));
+        } else if (const float qs = fmaf(ax, k.fshape, -k.fs_lo); VM == 1 || __any_sync(OCD_FULL, qs > 0.0f)) {
+            // in shape-scaled units qs = shape q: T = F1/(F1+F2) = 1/(1 + exp(r1 - r2)), r1 = 1/qs,
+            // r2 = 1/(shape width - qs); dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping qs and its
+            // complement to a tiny positive number makes the exponential saturate: T = 0, dT = 0 below the
+            // ramp and T = 1, dT = 0 above it, so the three regions need no branch.
+            const float r1 = Mth<false>::rcp_(fmaxf(qs, 1e-7f));
+            const float r2 = Mth<false>::rcp_(fmaxf(k.fs_w - qs, 1e-7f));
             const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_((r1 - r2) * OCD_LOG2E));
             const float dT = (T * (1.0f - T)) * (k.fshape * fmaf(r1, r1, r2 * r2));
             gx = fmaf(w.wfence, copysignf(fmaf(dT, ax, T), x), gx);
@@ -873,8 +909,9 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
                 th = fmaf(oc, k.dt, th);
                 Mth<PRECISE>::sincos_(th, sn, cs);
                 bool unused = false;
-                feature_grad<NOT_, LT, PRECISE, LIN>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P, gx[i], gy[i],
-                                                     gv[i], gth[i], tbase + (float)(i + 1), unused);
+                feature_grad<NOT_, LT, PRECISE, LIN, 0, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
+                                                                      gx[i], gy[i], gv[i], gth[i],
+                                                                      tbase + (float)(i + 1), unused);
             }
         }
 #pragma unroll

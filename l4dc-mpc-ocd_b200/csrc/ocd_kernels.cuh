@@ -20,6 +20,11 @@
 
 namespace ocd {
 
+// Register budgets.  The register-resident kernels (HT > 0) are built for four 192-thread blocks per SM
+// (<= 80 registers: 24 warps of the bench shape), the segmented kernels for three (96 registers: five warps
+// per SM sub-partition; 104 registers with no spills was measured and loses a warp per sub-partition at
+// H = 15 for a 1.6 % gain at H = 50), the latency variants take what they need.
+#define OCD_KERNEL_BOUNDS(HT, LAT) __launch_bounds__(kMaxThreads, (LAT) ? 1 : ((HT) == 0 ? 3 : 4))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -145,7 +150,7 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // ---------------------------------------------------------------------------------------------
 // LAT: the latency variant (straight-line forward sweep, see sgd_iteration), launched for small batches.
 template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
-__global__ void __launch_bounds__(kMaxThreads, LAT ? 1 : (HT == 0 ? 3 : 4))
+__global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
@@ -226,7 +231,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
 // k_episode
 // ---------------------------------------------------------------------------------------------
 template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
-__global__ void __launch_bounds__(kMaxThreads, LAT ? 1 : (HT == 0 ? 3 : 4))
+__global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ float smem_raw[];
     constexpr int P = kP;
