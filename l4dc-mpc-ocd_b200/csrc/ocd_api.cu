@@ -358,6 +358,12 @@ static int digest(const ocd_params *p, KParams &k) {
     k.mu = (float)p->friction;
     k.ts = (float)p->target_speed;               // np.float32(target_speed), merging.py:49
     k.bound = (float)(4.0 * (double)k.ts * (double)k.ts);
+    {   // float squaring is monotone, so the mask e*e <= bound (TF's Minimum gradient) is |e| <= ebound exactly
+        float e = sqrtf(k.bound);
+        while (e > 0.0f && e * e > k.bound) e = nextafterf(e, 0.0f);
+        while (nextafterf(e, INFINITY) * nextafterf(e, INFINITY) <= k.bound) e = nextafterf(e, INFINITY);
+        k.ebound = e;
+    }
     k.thr_lo = (float)(0.05 * (double)p->num_lanes - 0.05);   // threshold - width, math_utils.py:92
     k.thr_w = 0.05f;
     k.fshape = (float)(5.0 / 0.05);

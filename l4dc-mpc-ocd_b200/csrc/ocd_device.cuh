@@ -37,6 +37,7 @@ struct KParams {
     int   H, NO, L, K, n_iter, S, other_mode, extra_inits, optimizer;
     float lr, dt, dt2, hdt2;      // dt2 = (float)(dt*dt) squared in double; hdt2 = 0.5f*dt2
     float mu, ts, bound;          // friction, target speed, 4*ts^2
+    float ebound;                 // the largest float e with e*e <= bound in float32: |e| <= ebound <=> e*e <= bound
     float thr_lo, thr_w, fshape;  // fence ramp: |x| in [thr_lo, thr_lo + thr_w], shape = 5/width
     float turn;                   // 5*0.13 start angular velocity
     float lane_x[OCD_MAX_LANES];
@@ -336,7 +337,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
     // speed: min((v sin th - ts)^2, 4 ts^2)                                  merging.py:58-59
     {
         const float e = fmaf(v, sn, -k.ts);
-        const float ke = (e * e <= k.bound) ? (w.w0x2 * e) : 0.0f;
+        const float ke = (fabsf(e) <= k.ebound) ? (w.w0x2 * e) : 0.0f;      // e*e <= bound, without the square
         gv = RAWG ? ke : ke * sn;
         gth = RAWG ? 0.0f : (ke * v) * cs;
     }
