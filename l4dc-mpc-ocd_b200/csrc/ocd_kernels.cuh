@@ -20,11 +20,13 @@
 
 namespace ocd {
 
-// Register budgets.  The register-resident kernels (HT > 0) are built for four 192-thread blocks per SM
-// (<= 80 registers: 24 warps of the bench shape), the segmented kernels for three (96 registers: five warps
-// per SM sub-partition; 104 registers with no spills was measured and loses a warp per sub-partition at
-// H = 15 for a 1.6 % gain at H = 50), the latency variants take what they need.
-#define OCD_KERNEL_BOUNDS(HT, LAT) __launch_bounds__(kMaxThreads, (LAT) ? 1 : ((HT) == 0 ? 3 : 4))
+// Register budgets.  The register-resident kernels (HT > 0) are capped at 72 registers: seven warps per SM
+// sub-partition (nine 96-thread blocks per SM) instead of six at the 76-80 the code would like; the 24 bytes
+// of spill that costs are paid back by the extra warp (5.09 -> 4.97 ms at the bench shape; 64 registers /
+// eight warps measured no better).  The segmented kernels get 96 registers (five warps per sub-partition;
+// 104 registers with no spills loses a warp at H = 15 for a 1.6 % gain at H = 50), the latency variants take
+// what they need.
+#define OCD_KERNEL_BOUNDS(HT, LAT) __launch_bounds__(kMaxThreads, ((LAT) || (HT) > 0) ? 1 : 3) __maxnreg__((LAT) ? 255 : ((HT) > 0 ? 72 : 96))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
