@@ -847,6 +847,67 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 // so the cost over the register-resident kernel is one extra dynamics step (~15 %).  Controls
 // [H][2] and checkpoints [nseg][4] live in shared memory, thread index fastest.
 // ---------------------------------------------------------------------------------------------
+// Pass 2 of one segment: forward from the segment's start state with the feature gradients, then the reverse
+// sweep with the SGD update.  FULL: all SEG steps exist (no per-step predicates); otherwise the first `rem`.
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL>
+__device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
+                                          const float *os, int ostep, int P, float *us, int rem, float tbase,
+                                          float (&lam)[4]) {
+    float sn, cs;
+    Mth<PRECISE>::sincos_(th, sn, cs);
+    float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
+    const float *ot = os;
+#pragma unroll
+    for (int i = 0; i < SEG; ++i, ot += ostep) {
+        if (FULL || i < rem) {
+            ua[i] = us[2 * i];
+            uw[i] = us[2 * i + 1];
+            const float ac = fmaxf(fminf(ua[i], 4.0f), -8.0f);
+            const float oc = fmaxf(fminf(uw[i], 4.0f), -4.0f);
+            const float total = fmaf(-k.mu, v * v, ac);
+            const float dist = fmaf(total, k.hdt2, v * k.dt);
+            sv[i] = v; sc[i] = cs; ss[i] = sn; sd[i] = dist;
+            x = fmaf(cs, dist, x);
+            y = fmaf(sn, dist, y);
+            v = fmaf(total, k.dt, v);
+            th = fmaf(oc, k.dt, th);
+            Mth<PRECISE>::sincos_(th, sn, cs);
+            bool unused = false;
+            feature_grad<NOT_, LT, PRECISE, LIN, 0, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
+                                                                  gx[i], gy[i], gv[i], gth[i], tbase + (float)(i + 1),
+                                                                  unused);
+        }
+    }
+    float lx = lam[0], ly = lam[1], lv = lam[2], lth = lam[3];
+    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    const float lra = k.lr * k.hdt2, lrv = k.lr * k.dt;
+#pragma unroll
+    for (int ii = 0; ii < SEG; ++ii) {
+        const int i = SEG - 1 - ii;
+        if (FULL || i < rem) {
+            const float mx = gx[i] + lx, my = gy[i] + ly, mv = gv[i] + lv, mth = gth[i] + lth;
+            const float ld = fmaf(sc[i], mx, ss[i] * my);
+            const float a = ua[i], om = uw[i];
+            const bool in_a = (a >= -8.0f) && (a <= 4.0f);
+            const bool in_w = fabsf(om) <= 4.0f;
+            lv = fmaf(fmaf(c1, sv[i], 1.0f), mv, fmaf(c2, sv[i], k.dt) * ld);
+            lth = fmaf(sd[i], fmaf(sc[i], my, -(ss[i] * mx)), mth);
+            lx = mx;
+            ly = my;
+            if (PRECISE) {
+                const float ga = in_a ? fmaf(k.hdt2, ld, k.dt * mv) : 0.0f;
+                const float gw = in_w ? k.dt * mth : 0.0f;
+                us[2 * i] = fmaf(k.lr, ga, a);                 // u <- u - lr * d(-R)/du
+                us[2 * i + 1] = fmaf(k.lr, gw, om);
+            } else {                                           // the same with the constants folded
+                us[2 * i] = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
+                us[2 * i + 1] = in_w ? fmaf(lrv, mth, om) : om;
+            }
+        }
+    }
+    lam[0] = lx; lam[1] = ly; lam[2] = lv; lam[3] = lth;
+}
+
 template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN>
 __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                   float th0, const float *oth, int P, const SmemTraj &u, float *ck) {
@@ -876,64 +937,29 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             c[0] = x; c[1] = y; c[2] = v; c[3] = th;
         }
     }
-    float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
-    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    float lam[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // adjoint of (x, y, v, th)
     const int ostep = LIN ? 0 : NO * 2 * P;                    // slab floats per horizon step
     float *us = u.p + 2 * SEG * (nseg - 1);
     const float *c = ck + 4 * (nseg - 2);                      // checkpoint of the last segment (sg - 1)
     const float *os = oth + (size_t)SEG * (nseg - 1) * ostep;
     float tbase = (float)(SEG * (nseg - 1));                   // steps before this segment
-    int rem = H - SEG * (nseg - 1);                            // steps in this segment (last one may be short)
-#pragma unroll 1
-    for (int sg = nseg - 1; sg >= 0; --sg, us -= 2 * SEG, c -= 4, os -= SEG * ostep, rem = SEG, tbase -= (float)SEG) {
+    const int rem = H - SEG * (nseg - 1);                      // steps in the last segment (it may be short)
+    int sg = nseg - 1;
+    if (rem != SEG) {      // a short last segment is handled ahead of the loop: the loop body carries no predicates
         float x = x0, y = y0, v = v0, th = th0;
         if (sg > 0) {
             x = c[0]; y = c[1]; v = c[2]; th = c[3];
         }
-        float sn, cs;
-        Mth<PRECISE>::sincos_(th, sn, cs);
-        float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
-        const float *ot = os;
-#pragma unroll
-        for (int i = 0; i < SEG; ++i, ot += ostep) {
-            if (i < rem) {
-                ua[i] = us[2 * i];
-                uw[i] = us[2 * i + 1];
-                const float ac = fmaxf(fminf(ua[i], 4.0f), -8.0f);
-                const float oc = fmaxf(fminf(uw[i], 4.0f), -4.0f);
-                const float total = fmaf(-k.mu, v * v, ac);
-                const float dist = fmaf(total, k.hdt2, v * k.dt);
-                sv[i] = v; sc[i] = cs; ss[i] = sn; sd[i] = dist;
-                x = fmaf(cs, dist, x);
-                y = fmaf(sn, dist, y);
-                v = fmaf(total, k.dt, v);
-                th = fmaf(oc, k.dt, th);
-                Mth<PRECISE>::sincos_(th, sn, cs);
-                bool unused = false;
-                feature_grad<NOT_, LT, PRECISE, LIN, 0, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
-                                                                      gx[i], gy[i], gv[i], gth[i],
-                                                                      tbase + (float)(i + 1), unused);
-            }
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
+        --sg; us -= 2 * SEG; c -= 4; os -= SEG * ostep; tbase -= (float)SEG;
+    }
+#pragma unroll 1
+    for (; sg >= 0; --sg, us -= 2 * SEG, c -= 4, os -= SEG * ostep, tbase -= (float)SEG) {
+        float x = x0, y = y0, v = v0, th = th0;
+        if (sg > 0) {
+            x = c[0]; y = c[1]; v = c[2]; th = c[3];
         }
-#pragma unroll
-        for (int ii = 0; ii < SEG; ++ii) {
-            const int i = SEG - 1 - ii;
-            if (i < rem) {
-                const float mx = gx[i] + lx, my = gy[i] + ly, mv = gv[i] + lv, mth = gth[i] + lth;
-                const float ld = fmaf(sc[i], mx, ss[i] * my);
-                const float a = ua[i], om = uw[i];
-                const bool in_a = (a >= -8.0f) && (a <= 4.0f);
-                const bool in_w = fabsf(om) <= 4.0f;
-                lv = fmaf(fmaf(c1, sv[i], 1.0f), mv, fmaf(c2, sv[i], k.dt) * ld);
-                lth = fmaf(sd[i], fmaf(sc[i], my, -(ss[i] * mx)), mth);
-                lx = mx;
-                ly = my;
-                const float ga = in_a ? fmaf(k.hdt2, ld, k.dt * mv) : 0.0f;
-                const float gw = in_w ? k.dt * mth : 0.0f;
-                us[2 * i] = fmaf(k.lr, ga, a);                 // u <- u - lr * d(-R)/du
-                us[2 * i + 1] = fmaf(k.lr, gw, om);
-            }
-        }
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
     }
 }
 
