@@ -158,7 +158,7 @@ __device__ __forceinline__ float lbfgs_value_grad(const KParams &k, const GradW 
 }
 
 __global__ void __launch_bounds__(kMaxThreads) k_solve_lbfgs(const __grid_constant__ KParams k, const SolveArgs a) {
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;
     const Smem m = carve(smem_raw, k, P, false, false, false);
     const int p = threadIdx.x % P, s = threadIdx.x / P;

@@ -589,9 +589,9 @@ struct Traj {
 };
 
 // Controls of one thread kept in shared memory (used by the segmented solver for runtime / long
-// horizons, where 2H controls do not fit the register file).  Each thread owns 2H consecutive floats;
-// consecutive threads are an ODD number of floats apart, so a warp's accesses to the same (t, c) hit 32
-// different banks, while inside a segment every access is base + immediate.
+// horizons, where 2H controls do not fit the register file).  Each thread owns 2H consecutive floats; rows are
+// 2 x (odd) floats apart (seg_u_stride), so the 64-bit accesses of a warp to the same step are conflict-free,
+// while inside a segment every access is base + immediate.
 struct SmemTraj {
     float *p;      // this thread's controls: (acc_t, ang_t) at p[2t], p[2t+1]
     __device__ __forceinline__ float acc(int t) const { return p[2 * t]; }
@@ -601,11 +601,14 @@ struct SmemTraj {
         p[2 * t + 1] = w;
     }
 };
-__host__ __device__ inline int seg_u_stride(int H) { return (2 * H) | 1; }
+// Row strides (in floats) of a thread's controls and checkpoints.  A control pair is read and written as one
+// 64-bit access, a checkpoint as one 128-bit access, so rows are 8 / 16 bytes aligned and the stride is 2 x odd /
+// 4 x odd: the 16 (8) threads such an access is split over then hit 32 different banks.
+__host__ __device__ inline int seg_u_stride(int H) { return 2 * (H | 1); }
 // one checkpoint per segment but the first (which starts at the initial state); never zero floats
 __host__ __device__ inline int seg_ck_stride(int H, int SEG) {
     const int nseg = (H + SEG - 1) / SEG;
-    return (4 * (nseg > 1 ? nseg - 1 : 1)) | 1;
+    return 4 * ((nseg > 1 ? nseg - 1 : 1) | 1);
 }
 
 // Forward half of one iteration: roll the robot out and, at every new state, take the gradient of w.phi.
@@ -860,8 +863,9 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
 #pragma unroll
     for (int i = 0; i < SEG; ++i, ot += ostep) {
         if (FULL || i < rem) {
-            ua[i] = us[2 * i];
-            uw[i] = us[2 * i + 1];
+            const float2 uu = *reinterpret_cast<const float2 *>(us + 2 * i);
+            ua[i] = uu.x;
+            uw[i] = uu.y;
             const float ac = fmaxf(fminf(ua[i], 4.0f), -8.0f);
             const float oc = fmaxf(fminf(uw[i], 4.0f), -4.0f);
             const float total = fmaf(-k.mu, v * v, ac);
@@ -897,11 +901,11 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
             if (PRECISE) {
                 const float ga = in_a ? fmaf(k.hdt2, ld, k.dt * mv) : 0.0f;
                 const float gw = in_w ? k.dt * mth : 0.0f;
-                us[2 * i] = fmaf(k.lr, ga, a);                 // u <- u - lr * d(-R)/du
-                us[2 * i + 1] = fmaf(k.lr, gw, om);
+                *reinterpret_cast<float2 *>(us + 2 * i) =         // u <- u - lr * d(-R)/du
+                    make_float2(fmaf(k.lr, ga, a), fmaf(k.lr, gw, om));
             } else {                                           // the same with the constants folded
-                us[2 * i] = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
-                us[2 * i + 1] = in_w ? fmaf(lrv, mth, om) : om;
+                *reinterpret_cast<float2 *>(us + 2 * i) =
+                    make_float2(in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a, in_w ? fmaf(lrv, mth, om) : om);
             }
         }
     }
@@ -925,8 +929,9 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             for (int i = 0; i < SEG; ++i) {
                 float sn, cs;
                 Mth<PRECISE>::sincos_(th, sn, cs);
-                const float ac = fmaxf(fminf(us[2 * i], 4.0f), -8.0f);
-                const float oc = fmaxf(fminf(us[2 * i + 1], 4.0f), -4.0f);
+                const float2 uu = *reinterpret_cast<const float2 *>(us + 2 * i);
+                const float ac = fmaxf(fminf(uu.x, 4.0f), -8.0f);
+                const float oc = fmaxf(fminf(uu.y, 4.0f), -4.0f);
                 const float total = fmaf(-k.mu, v * v, ac);
                 const float dist = fmaf(total, k.hdt2, v * k.dt);
                 x = fmaf(cs, dist, x);
@@ -934,7 +939,7 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
                 v = fmaf(total, k.dt, v);
                 th = fmaf(oc, k.dt, th);
             }
-            c[0] = x; c[1] = y; c[2] = v; c[3] = th;
+            *reinterpret_cast<float4 *>(c) = make_float4(x, y, v, th);
         }
     }
     float lam[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // adjoint of (x, y, v, th)
@@ -948,7 +953,8 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
     if (rem != SEG) {      // a short last segment is handled ahead of the loop: the loop body carries no predicates
         float x = x0, y = y0, v = v0, th = th0;
         if (sg > 0) {
-            x = c[0]; y = c[1]; v = c[2]; th = c[3];
+            const float4 st = *reinterpret_cast<const float4 *>(c);
+            x = st.x; y = st.y; v = st.z; th = st.w;
         }
         seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
         --sg; us -= 2 * SEG; c -= 4; os -= SEG * ostep; tbase -= (float)SEG;
@@ -957,7 +963,8 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
     for (; sg >= 0; --sg, us -= 2 * SEG, c -= 4, os -= SEG * ostep, tbase -= (float)SEG) {
         float x = x0, y = y0, v = v0, th = th0;
         if (sg > 0) {
-            x = c[0]; y = c[1]; v = c[2]; th = c[3];
+            const float4 st = *reinterpret_cast<const float4 *>(c);
+            x = st.x; y = st.y; v = st.z; th = st.w;
         }
         seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
     }

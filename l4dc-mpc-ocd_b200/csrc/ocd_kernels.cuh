@@ -154,7 +154,7 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
 __global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
     constexpr bool SEGK = (HT == 0);     // runtime horizon: segmented adjoint, controls in shared memory
     const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
@@ -235,7 +235,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
 template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
 __global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;
     constexpr bool SEGK = (HT == 0);
     const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
@@ -379,7 +379,7 @@ __device__ __forceinline__ void tp_start_controls(const KParams &k, int s, float
 
 template <int HT, int NOT_, int LT>
 __global__ void __launch_bounds__(6 * kTP * kTG, 1) k_solve_tp(const __grid_constant__ KParams k, const SolveArgs a) {
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kTP;
     const Smem m = carve(smem_raw, k, P, false, false, false);
     const int t = threadIdx.x % kTG, g = threadIdx.x / kTG, p = g % P, s = g / P;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(6 * kTP * kTG, 1) k_solve_tp(const __grid_cons
 template <int HT, int NOT_, int LT>
 __global__ void __launch_bounds__(6 * kTP * kTG, 1)
 k_episode_tp(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kTP;
     const Smem m = carve(smem_raw, k, P, true, false, false);
     const int t = threadIdx.x % kTG, g = threadIdx.x / kTG, p = g % P, s = g / P;
