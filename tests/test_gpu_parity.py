@@ -578,6 +578,36 @@ def test_edge_shapes_vs_oracle(engine, H, C, lane_x, extra, other_mode, B):
         assert torch.equal(d["plan"], e["plan"])
 
 
+@pytest.mark.parametrize("H,C,extra,B", [(5, 2, False, 33), (5, 2, True, 1), (6, 2, False, 500), (5, 3, False, 4097),
+                                         (5, 6, False, 13001), (15, 2, False, 65), (14, 5, False, 2049),
+                                         (50, 6, False, 31), (64, 8, True, 3)])
+def test_outputs_stay_in_bounds(engine, H, C, extra, B):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds writes are looked for directly: every
+    output of the solve is a window inside a larger buffer filled with a sentinel, for ragged batch sizes that
+    reach each kernel form (time-parallel, latency, throughput, segmented); the guard bands must survive and
+    every element of the window must have been written."""
+    lane_x = (-0.1, 0.0, 0.1)
+    batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=H + C)
+    p = ocd.PlannerParams(H=H, C=C, n_iter=4, extra_inits=extra, lr=0.1 if H <= 6 else (0.03 if H <= 16 else 0.003))
+    dev = engine.device
+    world = torch.as_tensor(batch["world"], device=dev).permute(1, 2, 0).contiguous()
+    w = torch.as_tensor(batch["weights"], device=dev).t().contiguous()
+    idx = torch.as_tensor(batch["weight_idx"], device=dev)
+    G, SENT = 4096, 12345.0
+    shapes = dict(plan=(H * 2 * B, torch.float32), losses=(p.S * B, torch.float32), best=(B, torch.int32),
+                  all_plans=(p.S * H * 2 * B, torch.float32))
+    bufs = {k: torch.full((n + 2 * G,), SENT, dtype=dt, device=dev) for k, (n, dt) in shapes.items()}
+    out = dict(plan=bufs["plan"][G:G + H * 2 * B].view(H, 2, B), losses=bufs["losses"][G:G + p.S * B].view(p.S, B),
+               best=bufs["best"][G:G + B], all_plans=bufs["all_plans"][G:G + p.S * H * 2 * B].view(p.S, H, 2, B))
+    engine.solve_soa(p, world, w, w.shape[1], idx, all_plans=True, out=out)
+    torch.cuda.synchronize()
+    for k, (n, _) in shapes.items():
+        assert (bufs[k][:G] == SENT).all() and (bufs[k][G + n:] == SENT).all(), k
+        assert (bufs[k][G:G + n] != SENT).all(), k
+    assert torch.isfinite(out["plan"]).all() and torch.isfinite(out["losses"]).all()
+    assert ((out["best"] >= 0) & (out["best"] < p.S)).all()
+
+
 def test_nan_loss_follows_python_min(engine):
     """losses.index(min(losses)) (naive_planner.py:161-164): a NaN loss in slot 0 wins, later NaNs never do."""
     p = ocd.PlannerParams(n_iter=3)
