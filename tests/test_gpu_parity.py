@@ -608,6 +608,32 @@ def test_outputs_stay_in_bounds(engine, H, C, extra, B):
     assert ((out["best"] >= 0) & (out["best"] < p.S)).all()
 
 
+@pytest.mark.parametrize("name,B", [("finite_horizon", 7), ("replanning", 2999), ("local_opt", 20001)])
+def test_episode_outputs_stay_in_bounds(engine, name, B):
+    """The same for the episode kernel's outputs (returns, per-step traces, final world), for batch sizes that
+    reach its time-parallel, latency and throughput forms."""
+    spec = O.scenario_params(name)
+    p, sc = _pp(spec.params, ocd.MATH_FAST), _sc(spec.scenario)
+    p.n_iter = 3
+    T, Cc, dev = 4, p.C, engine.device
+    ri = torch.as_tensor(np.tile(spec.example_init.astype(np.float32), (B, 1)), device=dev).t().contiguous()
+    w = (spec.designer_weights / np.linalg.norm(spec.designer_weights)).astype(np.float32)
+    wt = torch.as_tensor(w, device=dev)
+    ul = torch.ones(B, dtype=torch.int32, device=dev) if name == "replanning" else None
+    G, SENT = 2048, 12345.0
+    shapes = dict(returns=(B, torch.float32), controls=(T * 2 * B, torch.float32), best=(T * B, torch.int32),
+                  states=(T * Cc * 4 * B, torch.float32), final_world=(Cc * 4 * B, torch.float32))
+    bufs = {k: torch.full((n + 2 * G,), SENT, dtype=dt, device=dev) for k, (n, dt) in shapes.items()}
+    view = dict(returns=(B,), controls=(T, 2, B), best=(T, B), states=(T, Cc, 4, B), final_world=(Cc, 4, B))
+    out = {k: bufs[k][G:G + shapes[k][0]].view(*view[k]) for k in shapes}
+    engine.episodes_soa(p, sc, ri, wt[:, None].contiguous(), 1, wt, T, unlucky_idx=ul, trace=True, final_world=True,
+                        out=out)
+    torch.cuda.synchronize()
+    for k, (n, _) in shapes.items():
+        assert (bufs[k][:G] == SENT).all() and (bufs[k][G + n:] == SENT).all(), k
+        assert (bufs[k][G:G + n] != SENT).all(), k
+
+
 def test_nan_loss_follows_python_min(engine):
     """losses.index(min(losses)) (naive_planner.py:161-164): a NaN loss in slot 0 wins, later NaNs never do."""
     p = ocd.PlannerParams(n_iter=3)
