@@ -14,7 +14,8 @@ Extra keys on the JSON line: roofline (FP32-pipe bound; the peak is measured in 
 dependent-free FMA kernel, since MEASURED_PEAKS.json has no FP32 figure), hbm (algorithmic bytes
 vs the measured copy bandwidth, to show the path is nowhere near memory-bound), e2e (same metric
 through the host-buffer C ABI, copies inside), cpu_baseline (the CPU oracle on this box's cores),
-cmaes (candidate-evals/s of the finite_horizon cmaes --n_inits 5 generation, one episode launch).
+cmaes (candidate-evals/s of the finite_horizon cmaes --n_inits 5 generation, one episode launch),
+horizons (solves/s at H = 15 and H = 50, the other horizons BASELINE's metric names).
 """
 from __future__ import annotations
 
@@ -321,6 +322,9 @@ def main():
         # ---- candidate-evals/s: one CMA-ES generation of finite_horizon cmaes --n_inits 5 -------------
         line["cmaes"] = cmaes_leg(eng, ocd, dist if distributed else None, rank, world_size, max_over_ranks, barrier)
 
+        # ---- the other horizons of the metric (H = 5..50): two points of BASELINE configs[4] -------------------
+        line["horizons"] = horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------
     if not args.no_extras and world_size == 1:
         threads = host_threads()
@@ -333,6 +337,34 @@ def main():
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak):
+    """H = 15 and H = 50 (2 cars, the sweep's learning rates), device-resident, a few launches each: the
+    segmented-adjoint kernels.  Same accounting as the headline: all ranks' solves / slowest rank's time."""
+    import torch
+    rows = []
+    for H, B, lr in ((15, 262144, 0.03), (50, 65536, 0.003)):
+        p = ocd.PlannerParams(H=H, C=2, lr=lr)
+        b = synthetic.make_batch(B, seed=99 + rank)
+        world = torch.as_tensor(b["world"], device=eng.device).permute(1, 2, 0).contiguous()
+        w = torch.as_tensor(b["weights"], device=eng.device).t().contiguous()
+        idx = torch.as_tensor(b["weight_idx"], device=eng.device)
+        out = eng.solve_soa(p, world, w, w.shape[1], idx)
+        barrier()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.solve_soa(p, world, w, w.shape[1], idx, out=out)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(float(e0.elapsed_time(e1))) / reps
+        fl = synthetic.flops_per_solve(H, 2, 3)
+        rows.append({"horizon": H, "problems_per_gpu": B, "lr": lr, "ms_per_launch": ms,
+                     "solves_per_sec": B * world_size / (ms * 1e-3),
+                     "frac_of_measured_fp32": fl * B / (ms * 1e-3) / fp32_peak})
+    return rows
 
 
 def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier):
