@@ -603,7 +603,6 @@ struct ocd_ctx {
     int device;
     cudaStream_t stream;                 // small calls (episodes)
     cudaStream_t lanes[kCtxStreams];     // the chunk pipeline of ocd_solve_batch_host
-    cudaEvent_t ready;                   // shared inputs (weights) are on the device
     cudaEvent_t loaded[kMaxChunks];      // chunk c's inputs are on the device
     cudaEvent_t solved[kMaxChunks];      // chunk c's kernel has finished
     cudaEvent_t done[kMaxChunks];        // chunk c's outputs are in host memory
@@ -638,7 +637,6 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < kCtxStreams; ++i)
         ok = ok && cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kMaxChunks; ++i)
         ok = ok && cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->loaded[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -659,7 +657,6 @@ void ocd_ctx_destroy(ocd_ctx *c) {
     if (c->pin) cudaFreeHost(c->pin);
     cudaStreamDestroy(c->stream);
     for (int i = 0; i < kCtxStreams; ++i) cudaStreamDestroy(c->lanes[i]);
-    cudaEventDestroy(c->ready);
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(c->done[i]);
         cudaEventDestroy(c->loaded[i]);
@@ -869,7 +866,6 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     if (n_oc && cudaMemcpyAsync(c->dev + o_oc, pin_oc ? (const char *)other_controls : c->pin + s_oc, n_oc,
                                 cudaMemcpyHostToDevice, s0) != cudaSuccess)
         return OCD_ECUDA;
-    if (cudaEventRecord(c->ready, s0) != cudaSuccess) return OCD_ECUDA;
 
     auto chunk_ptr = [&](const HostArray &a, int ch) -> char * {
         return a.user ? c->dev + a.dev_off + (size_t)a.rows * start[ch] * a.elem : nullptr;

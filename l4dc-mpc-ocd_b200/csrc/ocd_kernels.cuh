@@ -1,4 +1,4 @@
-// ocd_kernels.cuh -- the two planner kernels of the batched MPC engine and their launchers.
+// ocd_kernels.cuh -- the planner kernels of the batched MPC engine and their launchers.
 //
 //   k_solve    NaivePlanner.generate_plan for B problems: one thread per (problem, start); the
 //              block holds P problems x S starts, start-major (thread = s*P + p), so a warp runs
@@ -8,6 +8,10 @@
 //              block rebuilds the other cars' predicted tracks, runs the same solve, picks the
 //              first-minimum start, steps every car with the simulator dynamics and accumulates
 //              the true-weight reward of the past state.
+// Each exists in three forms picked at launch by the batch size: the throughput form above, its latency
+// variant (template flag LAT: straight-line forward sweep, registers spent on overlapping the horizon steps)
+// and the time-parallel form k_solve_tp / k_episode_tp (eight lanes per (problem, start), one horizon step
+// per lane).  Runtime horizons (HT == 0) use the segmented adjoint with controls in shared memory.
 // Each (H, other cars, math mode) specialisation is instantiated in its own translation unit
 // (ocd_inst.cu compiled with -DOCD_HT/-DOCD_NO/-DOCD_PRECISE) so the library builds in parallel.
 // Reference lines for each piece are cited in ocd_device.cuh and include/ocd_b200.h.
