@@ -579,7 +579,7 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
-    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
+    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     if constexpr (HAS_LAT && HT <= kTG) {
         if (tiny_batch(a.B, k.S)) {
             const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, false, false, false) * sizeof(float);
@@ -600,7 +600,7 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
-    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1 && NOT_ <= 2;
+    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     if constexpr (HAS_LAT && HT <= kTG) {
         if (tiny_batch(a.B, k.S)) {
             const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, true, false, false) * sizeof(float);

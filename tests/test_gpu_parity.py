@@ -506,7 +506,8 @@ def test_latency_variants_match_throughput_kernel(engine):
     (two other cars, two lanes), H=6 and the six-start set."""
     stats, ok = [], True
     for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
-                                    (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True)):
+                                    (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
+                                    (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False)):
         B = 32768 if extra else 65536
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
         p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra)
