@@ -850,15 +850,14 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 // so the cost over the register-resident kernel is one extra dynamics step (~15 %).  Controls
 // [H][2] and checkpoints [nseg][4] live in shared memory, thread index fastest.
 // ---------------------------------------------------------------------------------------------
-// Pass 2 of one segment: forward from the segment's start state with the feature gradients, then the reverse
-// sweep with the SGD update.  FULL: all SEG steps exist (no per-step predicates); otherwise the first `rem`.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL>
-__device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
-                                          const float *os, int ostep, int P, float *us, int rem, float tbase,
-                                          float (&lam)[4]) {
+// Forward half of pass 2 of one segment: from the segment's start state, with the feature gradients.
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int VM>
+__device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, float x, float y, float v, float th,
+                                            const float *os, int ostep, int P, const float *us, int rem, float tbase,
+                                            float *ua, float *uw, float *sv, float *sc, float *ss, float *sd, float *gx,
+                                            float *gy, float *gv, float *gth, bool &flag) {
     float sn, cs;
     Mth<PRECISE>::sincos_(th, sn, cs);
-    float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
     const float *ot = os;
 #pragma unroll
     for (int i = 0; i < SEG; ++i, ot += ostep) {
@@ -876,11 +875,31 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
             v = fmaf(total, k.dt, v);
             th = fmaf(oc, k.dt, th);
             Mth<PRECISE>::sincos_(th, sn, cs);
-            bool unused = false;
-            feature_grad<NOT_, LT, PRECISE, LIN, 0, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
-                                                                  gx[i], gy[i], gv[i], gth[i], tbase + (float)(i + 1),
-                                                                  unused);
+            feature_grad<NOT_, LT, PRECISE, LIN, VM, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
+                                                                   gx[i], gy[i], gv[i], gth[i], tbase + (float)(i + 1),
+                                                                   flag);
         }
+    }
+}
+
+// Pass 2 of one segment: the forward half above, then the reverse sweep with the SGD update.  FULL: all SEG
+// steps exist (no per-step predicates); otherwise the first `rem`.  LAT (small batches, FAST): the forward half
+// runs straight-line (vote mode 1) and is repeated with the exact rules if a lane asked for one.
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, bool LAT>
+__device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
+                                          const float *os, int ostep, int P, float *us, int rem, float tbase,
+                                          float (&lam)[4]) {
+    float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
+    bool flag = false;
+    if (LAT && !PRECISE) {
+        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 1>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv, sc,
+                                                          ss, sd, gx, gy, gv, gth, flag);
+        if (__any_sync(OCD_FULL, flag))
+            seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv,
+                                                              sc, ss, sd, gx, gy, gv, gth, flag);
+    } else {
+        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv, sc,
+                                                          ss, sd, gx, gy, gv, gth, flag);
     }
     float lx = lam[0], ly = lam[1], lv = lam[2], lth = lam[3];
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
@@ -912,7 +931,7 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
     lam[0] = lx; lam[1] = ly; lam[2] = lv; lam[3] = lth;
 }
 
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool LAT = false>
 __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                   float th0, const float *oth, int P, const SmemTraj &u, float *ck) {
     const int H = k.H;
@@ -956,7 +975,7 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             const float4 st = *reinterpret_cast<const float4 *>(c);
             x = st.x; y = st.y; v = st.z; th = st.w;
         }
-        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false, LAT>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
         --sg; us -= 2 * SEG; c -= 4; os -= SEG * ostep; tbase -= (float)SEG;
     }
 #pragma unroll 1
@@ -966,12 +985,12 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             const float4 st = *reinterpret_cast<const float4 *>(c);
             x = st.x; y = st.y; v = st.z; th = st.w;
         }
-        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true, LAT>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
     }
 }
 
 // The complete segmented solve for one (problem, start): start controls, n_iter iterations, final loss.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool LAT = false>
 __device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &w, const float *wraw, int ws,
                                                  float x0, float y0, float v0, float th0, const float *oth, int P,
                                                  int s, float cur_speed, const SmemTraj &u, float *ck) {
@@ -983,7 +1002,7 @@ __device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &
     }
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
-        sgd_iteration_seg<SEG, NOT_, LT, PRECISE, LIN>(k, w, x0, y0, v0, th0, oth, P, u, ck);
+        sgd_iteration_seg<SEG, NOT_, LT, PRECISE, LIN, LAT>(k, w, x0, y0, v0, th0, oth, P, u, ck);
     return -rollout_reward<0, LT, PRECISE, SmemTraj, LIN>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 

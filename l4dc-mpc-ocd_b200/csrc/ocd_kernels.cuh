@@ -195,10 +195,10 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     if (SEGK) {
         float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
         loss = (!PRECISE && lin)
-                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p,
-                                                                         P, s, speed, us, ck)
-                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
-                                                                     s, speed, us, ck);
+                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                              m.oth + p, P, s, speed, us, ck)
+                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                          m.oth + p, P, s, speed, us, ck);
     } else {
         init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
         loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
@@ -587,8 +587,9 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
             return cuda_status();
         }
     }
+    constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT>;
+    if ((HAS_LAT || SEG_LAT) && small_batch(a.B, a.P, k.S)) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT || SEG_LAT>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);

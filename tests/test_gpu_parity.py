@@ -503,14 +503,17 @@ def test_latency_variants_match_throughput_kernel(engine):
     """Up to ~1 500 problems run the time-parallel kernel (8 lanes per start), up to ~12 600 the latency
     variant (straight-line forward sweep, no votes), larger batches the throughput kernel: the same
     problems must get the same answer whichever runs.  Covers the finite_horizon shape, the replanning shape
-    (two other cars, two lanes), H=6 and the six-start set."""
+    (two other cars, two lanes), H=6, the six-start set, many cars, and the segmented kernels (H = 12, 15: latency
+    variant only)."""
     stats, ok = [], True
     for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
-                                    (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False)):
+                                    (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False),
+                                    (2, (-0.1, 0.0, 0.1), 1.0, 15, False), (5, (-0.1, 0.0, 0.1), 1.0, 12, False)):
         B = 32768 if extra else 65536
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
-        p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra)
+        p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra,
+                              lr=0.1 if H <= 6 else 0.03)
         big = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"], all_plans=True)
         for n in (4096, 500):
             small = engine.solve(p, batch["world"][:n], batch["weights"], weight_idx=batch["weight_idx"][:n],
@@ -518,10 +521,13 @@ def test_latency_variants_match_throughput_kernel(engine):
             same = (big["all_plans"][:n] == small["all_plans"]).flatten(1).all(dim=1)
             close = (big["plan"][:n] - small["plan"]).abs().amax(dim=(1, 2)) <= 1e-3
             stats.append((C, H, extra, n, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
-            ok = ok and same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
+            if H <= 8:      # the register-resident forms are bit-identical
+                ok = ok and same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
+            else:           # the segmented kernel's latency variant fuses multiply-adds differently: same plans to
+                ok = ok and close.float().mean().item() >= 0.98          # tolerance, up to ill-conditioned problems
             ok = ok and torch.equal(big["best"][:n][same], small["best"][same])
             ok = ok and torch.equal(big["losses"][:n][same], small["losses"][same])
-    assert ok, stats
+    assert ok, stats[-8:]
 
 
 # ---- edge shapes: limits of the ABI, ragged batches, every weight / control sharing mode -----------------
