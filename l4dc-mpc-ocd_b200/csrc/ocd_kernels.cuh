@@ -19,6 +19,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ocd_b200.h"
 #include "ocd_device.cuh"
 
@@ -569,11 +571,31 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
-// A batch is "small" when its warps cannot hide each other's latency: at most two per SM sub-partition
-// of a 148-SM part.  The compile-time-horizon FAST kernels then run their latency variant.
-inline bool small_batch(long long B, int P, int S) { return ((B + P - 1) / P) * S <= 2 * 4 * 148; }
-// ... and "tiny" when the same holds with eight lanes per (problem, start): the time-parallel kernels.
-inline bool tiny_batch(long long B, int S) { return ((B + kTP - 1) / kTP) * S <= 2 * 4 * 148; }
+// Which form runs (measured on B200, scratch/form_sweep*.py; times in DESIGN.md):
+//  * time-parallel: up to ~800 warps of 4 starts (about 1 000 problems) -- below that its shorter dependent chain
+//    wins, above it its 4x instruction count per solve loses;
+//  * latency variant: up to 4 096 warps (about 43 000 problems).  With 12 warps per SM it keeps up with the
+//    throughput form far beyond the point where the GPU is full (equal at 5*10^5 problems for 2 cars), but loses
+//    from ~6*10^4 problems with many cars or H = 15, so the switch sits below that;
+//  * segmented kernels whose shared memory (controls + checkpoints) leaves at most four blocks per SM anyway
+//    (H >= ~40): the latency variant at every size (H = 50: 4-11 % faster up to 2.6*10^5 problems);
+//  * throughput form otherwise.
+// OCD_KERNEL_FORM=throughput|latency|tp overrides the choice (tests and tuning; read at every launch).
+inline int forced_form() {
+    const char *e = std::getenv("OCD_KERNEL_FORM");
+    if (!e) return 0;
+    return e[0] == 't' && e[1] == 'h' ? 1 : (e[0] == 'l' ? 2 : (e[0] == 't' && e[1] == 'p' ? 3 : 0));
+}
+inline bool small_batch(long long B, int P, int S, size_t smem_bytes = 0) {
+    const int f = forced_form();
+    if (f) return f == 2;
+    if (smem_bytes && (227u * 1024u) / (smem_bytes + 1024u) <= 4) return true;
+    return ((B + P - 1) / P) * S <= 4096;
+}
+inline bool tiny_batch(long long B, int S) {
+    const int f = forced_form();
+    return f ? f == 3 : ((B + kTP - 1) / kTP) * S <= 800;
+}
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
@@ -589,7 +611,8 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     }
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    if ((HAS_LAT || SEG_LAT) && small_batch(a.B, a.P, k.S)) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT || SEG_LAT>;
+    if ((HAS_LAT || SEG_LAT) && small_batch(a.B, a.P, k.S, SEG_LAT ? bytes : 0))
+        kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT || SEG_LAT>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);

@@ -586,7 +586,8 @@ def test_edge_shapes_vs_oracle(engine, H, C, lane_x, extra, other_mode, B):
 
 
 @pytest.mark.parametrize("H,C,extra,B", [(5, 2, False, 33), (5, 2, True, 1), (6, 2, False, 500), (5, 3, False, 4097),
-                                         (5, 6, False, 13001), (15, 2, False, 65), (14, 5, False, 2049),
+                                         (5, 6, False, 13001), (5, 2, False, 70001), (5, 5, True, 30001),
+                                         (15, 2, False, 65), (14, 5, False, 2049), (15, 3, False, 50001),
                                          (50, 6, False, 31), (64, 8, True, 3)])
 def test_outputs_stay_in_bounds(engine, H, C, extra, B):
     """compute-sanitizer is not available on the GPU pool, so out-of-bounds writes are looked for directly: every
