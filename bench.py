@@ -262,7 +262,7 @@ def main():
                 "frac": achieved_tf / (fp32_peak / 1e12), "traffic": traffic,
                 "peak_source": "dependent-free FFMA kernel measured in this job (MEASURED_PEAKS.json has no FP32 figure)",
                 "nominal_peak": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
-                "flops_per_solve": flops, "kernel": "k_solve<5,1,fast>", "kernel_ms": own_ms}
+                "flops_per_solve": flops, "kernel": "k_solve<5,1,3,fast,wide>", "kernel_ms": own_ms}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm = {"achieved": hbm_bytes * B / (own_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
            "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback",

@@ -26,13 +26,17 @@
 
 namespace ocd {
 
-// Register budgets.  The register-resident kernels (HT > 0) are capped at 72 registers: seven warps per SM
-// sub-partition (nine 96-thread blocks per SM) instead of six at the 76-80 the code would like; the 24 bytes
-// of spill that costs are paid back by the extra warp (5.09 -> 4.97 ms at the bench shape; 64 registers /
-// eight warps measured no better).  The segmented kernels get 96 registers (five warps per sub-partition;
-// 104 registers with no spills loses a warp at H = 15 for a 1.6 % gain at H = 50), the latency variants take
-// what they need.
-#define OCD_KERNEL_BOUNDS(HT, LAT) __launch_bounds__(kMaxThreads, ((LAT) || (HT) > 0) ? 1 : 3) __maxnreg__((LAT) ? 255 : ((HT) > 0 ? 72 : 96))
+// Register budgets (LAT is the kernel form: 0 throughput, 1 latency, 2 wide).  The register-resident throughput
+// kernels (HT > 0) are capped at 72 registers: seven warps per SM sub-partition (nine 96-thread blocks per SM)
+// instead of six at the 76-80 the code would like; the 24 bytes of spill that costs are paid back by the extra
+// warp (5.09 -> 4.97 ms at the bench shape; 64 registers / eight warps measured no better).  The segmented
+// kernels get 96 registers (five warps per sub-partition; 104 registers with no spills loses a warp at H = 15 for
+// a 1.6 % gain at H = 50).  The latency form takes what it needs (140-250); the wide form is the same straight-line
+// code held to 128 registers -- four warps per sub-partition -- which is what makes it the fastest form for large
+// batches of the one-other-car shapes (4.77 ms at the bench shape).
+#define OCD_KERNEL_BOUNDS(HT, LAT)                                        \
+    __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
+    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? 128 : ((HT) > 0 ? 72 : 96)))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -156,8 +160,9 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // ---------------------------------------------------------------------------------------------
 // k_solve
 // ---------------------------------------------------------------------------------------------
-// LAT: the latency variant (straight-line forward sweep, see sgd_iteration), launched for small batches.
-template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
+// LAT != 0: the straight-line forward sweep (see sgd_iteration): 1 the latency form launched for small batches,
+// 2 the wide form (same code, 128 registers) launched for large batches of the one-other-car shapes.
+template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
 __global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
@@ -197,13 +202,13 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     if (SEGK) {
         float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
         loss = (!PRECISE && lin)
-                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                               m.oth + p, P, s, speed, us, ck)
-                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                           m.oth + p, P, s, speed, us, ck);
     } else {
         init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
-        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
+        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
                                                                       u);
     }
     m.loss[s * P + p] = loss;
@@ -238,7 +243,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
 // ---------------------------------------------------------------------------------------------
 // k_episode
 // ---------------------------------------------------------------------------------------------
-template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
+template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
 __global__ void OCD_KERNEL_BOUNDS(HT, LAT)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
@@ -322,7 +327,7 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
                                                                          m.oth + p, P, s, v0, us, ck);
         } else {
             init_start<(HT > 0 ? HT : 1)>(k, s, v0, u);
-            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                            m.oth + p, P, u);
         }
         m.loss[s * P + p] = loss;
@@ -571,30 +576,42 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
-// Which form runs (measured on B200, scratch/form_sweep*.py; times in DESIGN.md):
+// Which form runs (measured on B200, scratch/form_sweep*.py, scratch/form_ep.py; times in DESIGN.md):
 //  * time-parallel: up to ~800 warps of 4 starts (about 1 000 problems) -- below that its shorter dependent chain
 //    wins, above it its 4x instruction count per solve loses;
-//  * latency variant: up to 4 096 warps (about 43 000 problems).  With 12 warps per SM it keeps up with the
-//    throughput form far beyond the point where the GPU is full (equal at 5*10^5 problems for 2 cars), but loses
-//    from ~6*10^4 problems with many cars or H = 15, so the switch sits below that;
-//  * segmented kernels whose shared memory (controls + checkpoints) leaves at most four blocks per SM anyway
-//    (H >= ~40): the latency variant at every size (H = 50: 4-11 % faster up to 2.6*10^5 problems);
+//  * latency form: up to 2 048 warps (about 21 000 problems): one wave of its four blocks per SM;
+//  * one other car (the bench shape, finite_horizon, local_opt, H = 6): beyond that the WIDE form -- the same
+//    straight-line code at 128 registers, 15 warps per SM.  It beats the vote-guarded throughput form at every
+//    size for solves (4.77 vs 4.96 ms at 2^20 problems); for whole episodes it wins up to ~10^5 worlds and
+//    loses a few per cent beyond, so episodes go back to the throughput form above 8 192 warps;
+//  * more cars: the latency form up to 4 096 warps (its spills cost more than its ILP gains beyond), then the
+//    throughput form;
+//  * segmented kernels: latency form up to 4 096 warps, and at every size when shared memory (controls +
+//    checkpoints) leaves at most four blocks per SM anyway (H >= ~40; H = 50: 4-11 % faster);
 //  * throughput form otherwise.
-// OCD_KERNEL_FORM=throughput|latency|tp overrides the choice (tests and tuning; read at every launch).
+// OCD_KERNEL_FORM=throughput|latency|wide|tp overrides the choice (tests and tuning; read at every launch).
+enum { kFormAuto = 0, kFormThroughput, kFormLatency, kFormTp, kFormWide };
 inline int forced_form() {
     const char *e = std::getenv("OCD_KERNEL_FORM");
-    if (!e) return 0;
-    return e[0] == 't' && e[1] == 'h' ? 1 : (e[0] == 'l' ? 2 : (e[0] == 't' && e[1] == 'p' ? 3 : 0));
+    if (!e) return kFormAuto;
+    if (e[0] == 't') return e[1] == 'h' ? kFormThroughput : (e[1] == 'p' ? kFormTp : kFormAuto);
+    return e[0] == 'l' ? kFormLatency : (e[0] == 'w' ? kFormWide : kFormAuto);
 }
-inline bool small_batch(long long B, int P, int S, size_t smem_bytes = 0) {
-    const int f = forced_form();
-    if (f) return f == 2;
-    if (smem_bytes && (227u * 1024u) / (smem_bytes + 1024u) <= 4) return true;
-    return ((B + P - 1) / P) * S <= 4096;
-}
+inline long long batch_warps(long long B, int P, int S) { return ((B + P - 1) / P) * S; }
 inline bool tiny_batch(long long B, int S) {
     const int f = forced_form();
-    return f ? f == 3 : ((B + kTP - 1) / kTP) * S <= 800;
+    return f ? f == kFormTp : batch_warps(B, kTP, S) <= 800;
+}
+// -> 0 throughput, 1 latency, 2 wide.  has_wide: the kernel has a wide form (compile-time horizon, one other car).
+inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool episode, size_t seg_smem_bytes) {
+    const int f = forced_form();
+    if (f == kFormThroughput || !has_lat) return 0;
+    if (f == kFormLatency) return 1;
+    if (f == kFormWide) return has_wide ? 2 : 1;
+    const long long w = batch_warps(B, P, S);
+    if (seg_smem_bytes && (227u * 1024u) / (seg_smem_bytes + 1024u) <= 4) return 1;
+    if (has_wide) return w <= 2048 ? 1 : ((!episode || w <= 8192) ? 2 : 0);
+    return w <= 4096 ? 1 : 0;
 }
 
 template <int HT, int NOT_, int LT, bool PRECISE>
@@ -610,9 +627,11 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
         }
     }
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
+    constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    if ((HAS_LAT || SEG_LAT) && small_batch(a.B, a.P, k.S, SEG_LAT ? bytes : 0))
-        kern = k_solve<HT, NOT_, LT, PRECISE, HAS_LAT || SEG_LAT>;
+    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, false, SEG_LAT ? bytes : 0);
+    if (form == 1) kern = k_solve<HT, NOT_, LT, PRECISE, (HAS_LAT || SEG_LAT) ? 1 : 0>;
+    if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
@@ -633,7 +652,10 @@ int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs
         }
     }
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
-    if (HAS_LAT && small_batch(a.B, a.P, k.S)) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT>;
+    constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
+    const int form = pick_form(a.B, a.P, k.S, HAS_LAT, HAS_WIDE, true, 0);
+    if (form == 1) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT ? 1 : 0>;
+    if (form == 2) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);

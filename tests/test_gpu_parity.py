@@ -499,35 +499,53 @@ def test_full_size_properties(engine):
     assert np.max(np.abs(got[same] - ref["plan"][same])) <= 1e-3
 
 
-def test_latency_variants_match_throughput_kernel(engine):
-    """Up to ~1 500 problems run the time-parallel kernel (8 lanes per start), up to ~12 600 the latency
-    variant (straight-line forward sweep, no votes), larger batches the throughput kernel: the same
-    problems must get the same answer whichever runs.  Covers the finite_horizon shape, the replanning shape
-    (two other cars, two lanes), H=6, the six-start set, many cars, and the segmented kernels (H = 12, 15: latency
-    variant only)."""
+def test_kernel_forms_agree(engine, monkeypatch):
+    """Every shape has up to four kernel forms, picked by batch size: time-parallel (8 lanes per start), latency
+    (straight-line forward sweep), wide (the same at 128 registers, one-other-car shapes) and throughput
+    (vote-guarded).  The same problems must get the same answer whichever runs: each form is forced through
+    OCD_KERNEL_FORM on the same 3 000 problems, and the automatic choice is checked at three batch sizes.
+    Covers the finite_horizon shape, the replanning shape (two other cars, two lanes), H = 6, the six-start set,
+    many cars, and the segmented kernels (H = 12, 15: throughput and latency forms, which fuse multiply-adds
+    differently -- same plans to tolerance, up to ill-conditioned problems)."""
     stats, ok = [], True
     for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
                                     (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 15, False), (5, (-0.1, 0.0, 0.1), 1.0, 12, False)):
-        B = 32768 if extra else 65536
+        B, n = (32768 if extra else 65536), 3000
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
         p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra,
                               lr=0.1 if H <= 6 else 0.03)
-        big = engine.solve(p, batch["world"], batch["weights"], weight_idx=batch["weight_idx"], all_plans=True)
-        for n in (4096, 500):
-            small = engine.solve(p, batch["world"][:n], batch["weights"], weight_idx=batch["weight_idx"][:n],
-                                 all_plans=True)
-            same = (big["all_plans"][:n] == small["all_plans"]).flatten(1).all(dim=1)
-            close = (big["plan"][:n] - small["plan"]).abs().amax(dim=(1, 2)) <= 1e-3
-            stats.append((C, H, extra, n, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
+
+        def solve(m):
+            return engine.solve(p, batch["world"][:m], batch["weights"], weight_idx=batch["weight_idx"][:m],
+                                all_plans=True)
+
+        monkeypatch.setenv("OCD_KERNEL_FORM", "throughput")
+        ref = solve(n)
+        others = {}
+        for form in ("latency", "wide", "tp"):
+            monkeypatch.setenv("OCD_KERNEL_FORM", form)
+            others[form] = solve(n)
+        monkeypatch.delenv("OCD_KERNEL_FORM")
+        for m in (500, n, B):                      # the automatic choice at three sizes
+            others[f"auto{m}"] = solve(m)
+        for name, res in others.items():
+            m = res["plan"].shape[0]
+            k = min(m, n)
+            same = (ref["all_plans"][:k] == res["all_plans"][:k]).flatten(1).all(dim=1)
+            close = (ref["plan"][:k] - res["plan"][:k]).abs().amax(dim=(1, 2)) <= 1e-3
+            stats.append((C, H, extra, name, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
             if H <= 8:      # the register-resident forms are bit-identical
-                ok = ok and same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
-            else:           # the segmented kernel's latency variant fuses multiply-adds differently: same plans to
-                ok = ok and close.float().mean().item() >= 0.98          # tolerance, up to ill-conditioned problems
-            ok = ok and torch.equal(big["best"][:n][same], small["best"][same])
-            ok = ok and torch.equal(big["losses"][:n][same], small["losses"][same])
-    assert ok, stats[-8:]
+                good = same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
+            else:
+                good = close.float().mean().item() >= 0.98
+            good = good and torch.equal(ref["best"][:k][same], res["best"][:k][same])
+            good = good and torch.equal(ref["losses"][:k][same], res["losses"][:k][same])
+            if not good:
+                ok = False
+                stats.append("^ FAILED")
+    assert ok, [st for i, st in enumerate(stats) if st == "^ FAILED" or (i + 1 < len(stats) and stats[i + 1] == "^ FAILED")]
 
 
 # ---- edge shapes: limits of the ABI, ragged batches, every weight / control sharing mode -----------------
