@@ -30,13 +30,13 @@ namespace ocd {
 // kernels (HT > 0) are capped at 72 registers: seven warps per SM sub-partition (nine 96-thread blocks per SM)
 // instead of six at the 76-80 the code would like; the 24 bytes of spill that costs are paid back by the extra
 // warp (5.09 -> 4.97 ms at the bench shape; 64 registers / eight warps measured no better).  The segmented
-// kernels get 96 registers (five warps per sub-partition; 104 registers with no spills loses a warp at H = 15 for
-// a 1.6 % gain at H = 50).  The latency form takes what it needs (140-250); the wide form is the same straight-line
-// code held to 128 registers -- four warps per sub-partition -- which is what makes it the fastest form for large
-// batches of the one-other-car shapes (4.77 ms at the bench shape).
-#define OCD_KERNEL_BOUNDS(HT, LAT)                                        \
+// throughput kernels get 96 registers (five warps per sub-partition).  The latency form takes what it needs
+// (140-250).  The wide form is the same straight-line code held to 128 registers with one other car (four warps
+// per sub-partition) and 168 with more (three): measured against 112 / 128 / 168 on every shape of the sweep
+// (scratch/wide_regs.sh); it is the fastest form for large batches of most shapes (see pick_form).
+#define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? 128 : ((HT) > 0 ? 72 : 96)))
+    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? ((NOT_) == 1 ? 128 : 168) : ((HT) > 0 ? 72 : 96)))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -163,7 +163,7 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // LAT != 0: the straight-line forward sweep (see sgd_iteration): 1 the latency form launched for small batches,
 // 2 the wide form (same code, 128 registers) launched for large batches of the one-other-car shapes.
 template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
-__global__ void OCD_KERNEL_BOUNDS(HT, LAT)
+__global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
@@ -244,7 +244,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
 // k_episode
 // ---------------------------------------------------------------------------------------------
 template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
-__global__ void OCD_KERNEL_BOUNDS(HT, LAT)
+__global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenario sc, const EpisodeArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;
@@ -576,19 +576,19 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
-// Which form runs (measured on B200, scratch/form_sweep*.py, scratch/form_ep.py; times in DESIGN.md):
+// Which form runs (measured on B200, scratch/form_sweep*.py, scratch/form_ep.py, scratch/wide_regs.sh; times in
+// DESIGN.md):
 //  * time-parallel: up to ~800 warps of 4 starts (about 1 000 problems) -- below that its shorter dependent chain
 //    wins, above it its 4x instruction count per solve loses;
-//  * latency form: up to 2 048 warps (about 21 000 problems): one wave of its four blocks per SM;
-//  * one other car (the bench shape, finite_horizon, local_opt, H = 6): beyond that the WIDE form -- the same
-//    straight-line code at 128 registers, 15 warps per SM.  It beats the vote-guarded throughput form at every
-//    size for solves (4.77 vs 4.96 ms at 2^20 problems); for whole episodes it wins up to ~10^5 worlds and
-//    loses a few per cent beyond, so episodes go back to the throughput form above 8 192 warps;
-//  * more cars: the latency form up to 4 096 warps (its spills cost more than its ILP gains beyond), then the
-//    throughput form;
-//  * segmented kernels: latency form up to 4 096 warps, and at every size when shared memory (controls +
-//    checkpoints) leaves at most four blocks per SM anyway (H >= ~40; H = 50: 4-11 % faster);
-//  * throughput form otherwise.
+//  * latency form: up to 2 048 warps (one other car: one wave of its four blocks per SM) or 4 096 warps;
+//  * beyond that the WIDE form -- the same straight-line code under a register cap -- wherever it beats the
+//    vote-guarded throughput form: compile-time horizons with one or two other cars (4.77 vs 4.96 ms at the
+//    bench shape, 6.29 vs 6.84 ms with three cars) and every segmented kernel (H = 15: 4.74 vs 5.88 ms at 2.6*10^5
+//    problems; H = 50: 4.37 vs 5.99 ms at 6.5*10^4).  Without the votes a horizon step is one basic block and the
+//    scheduler overlaps the steps; that is worth more than the throughput form's extra warps and skipped blocks;
+//  * throughput form: compile-time horizons with four or more cars (the wide form's spills cost more than it
+//    gains: 11.0 vs 9.57 ms with six cars), whole episodes beyond 8 192 warps (one other car) / 4 096 warps,
+//    PRECISE math, and when forced.
 // OCD_KERNEL_FORM=throughput|latency|wide|tp overrides the choice (tests and tuning; read at every launch).
 enum { kFormAuto = 0, kFormThroughput, kFormLatency, kFormTp, kFormWide };
 inline int forced_form() {
@@ -602,16 +602,17 @@ inline bool tiny_batch(long long B, int S) {
     const int f = forced_form();
     return f ? f == kFormTp : batch_warps(B, kTP, S) <= 800;
 }
-// -> 0 throughput, 1 latency, 2 wide.  has_wide: the kernel has a wide form (compile-time horizon, one other car).
-inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool episode, size_t seg_smem_bytes) {
+// -> 0 throughput, 1 latency, 2 wide.
+inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode) {
     const int f = forced_form();
     if (f == kFormThroughput || !has_lat) return 0;
     if (f == kFormLatency) return 1;
     if (f == kFormWide) return has_wide ? 2 : 1;
     const long long w = batch_warps(B, P, S);
-    if (seg_smem_bytes && (227u * 1024u) / (seg_smem_bytes + 1024u) <= 4) return 1;
-    if (has_wide) return w <= 2048 ? 1 : ((!episode || w <= 8192) ? 2 : 0);
-    return w <= 4096 ? 1 : 0;
+    if (w <= (one_other ? 2048 : 4096)) return 1;
+    if (!has_wide) return 0;
+    if (episode) return (one_other && w <= 8192) ? 2 : 0;
+    return 2;
 }
 
 template <int HT, int NOT_, int LT, bool PRECISE>
@@ -627,9 +628,9 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
         }
     }
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
-    constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
+    constexpr bool HAS_WIDE = (HAS_LAT && NOT_ <= 2) || SEG_LAT;
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, false, SEG_LAT ? bytes : 0);
+    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, HT > 0 && NOT_ == 1, false);
     if (form == 1) kern = k_solve<HT, NOT_, LT, PRECISE, (HAS_LAT || SEG_LAT) ? 1 : 0>;
     if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
@@ -653,7 +654,7 @@ int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs
     }
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
     constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
-    const int form = pick_form(a.B, a.P, k.S, HAS_LAT, HAS_WIDE, true, 0);
+    const int form = pick_form(a.B, a.P, k.S, HAS_LAT, HAS_WIDE, NOT_ == 1, true);
     if (form == 1) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT ? 1 : 0>;
     if (form == 2) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
