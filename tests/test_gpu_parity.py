@@ -376,7 +376,7 @@ def test_episode_single_step_is_world_step(engine):
 
 
 @pytest.mark.parametrize("name", ["finite_horizon", "replanning"])
-def test_episode_full_size_properties(engine, name):
+def test_episode_full_size_properties(engine, name, monkeypatch):
     """65 536 episodes (the throughput form of the episode kernel; the golden episodes run the time-parallel
     form): an episode of 6 control steps == two chained launches of 3, permuting the batch permutes the
     results, weight_idx indirection == expanded weights, the first 500 / 4 000 episodes alone (time-parallel /
@@ -412,6 +412,14 @@ def test_episode_full_size_properties(engine, name):
         assert same.float().mean().item() >= 0.995, (n, same.float().mean().item())
         assert ((small["returns"] - full["returns"][:n]).abs() <= 1e-3 * full["returns"][:n].abs().clamp(min=1e-3)) \
             .float().mean().item() >= 0.99
+    # ... and so does every form forced on the same 4 000 episodes
+    for form in ("throughput", "latency", "wide", "tp"):
+        monkeypatch.setenv("OCD_KERNEL_FORM", form)
+        forced = engine.episodes(p, sc, ri[:4000], cand, wt, T, weight_idx=widx[:4000],
+                                 unlucky_idx=None if ul is None else ul[:4000])
+        monkeypatch.delenv("OCD_KERNEL_FORM")
+        same = forced["returns"] == full["returns"][:4000]
+        assert same.float().mean().item() >= 0.995, (form, same.float().mean().item())
     # oracle spot checks
     sel = np.linspace(0, B - 1, 32).astype(np.int64)
     got = full["returns"].cpu().numpy()[sel]
