@@ -613,7 +613,11 @@ __host__ __device__ inline int seg_ck_stride(int H, int SEG) {
 
 // Forward half of one iteration: roll the robot out and, at every new state, take the gradient of w.phi.
 // Fills the saved per-step values the reverse sweep needs.  VM as in feature_grad.
-template <int HT, int NOT_, int LT, bool PRECISE, int VM>
+// SF (step fence; the wide form with three or more other cars): an opaque, always-true branch at the top of every
+// step keeps the steps in separate basic blocks.  The cars of one step still interleave, but the scheduler no
+// longer overlaps the five steps, which with many cars needs more registers than there are (544 bytes of spill
+// at 128 registers, none with the fence: 8.45 vs 11.0 ms with six cars, and 9.57 ms for the throughput form).
+template <int HT, int NOT_, int LT, bool PRECISE, int VM, bool SF = false>
 __device__ __forceinline__ void forward_sweep(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                               float th0, float sn0, float cs0, const float *oth, int P,
                                               const Traj<HT> &u, float *sv, float *sc, float *ss, float *sd,
@@ -623,6 +627,11 @@ __device__ __forceinline__ void forward_sweep(const KParams &k, const GradW &w, 
     float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
 #pragma unroll(HT > 0 ? HT : 1)
     for (int t = 0; t < H; ++t) {
+        if (SF) {
+            int one;
+            asm volatile("mov.u32 %0, 1;" : "=r"(one));
+            if (one == 0) continue;
+        }
         const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
         const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
         const float total = fmaf(-k.mu, v * v, ac);
@@ -641,7 +650,7 @@ __device__ __forceinline__ void forward_sweep(const KParams &k, const GradW &w, 
 // LAT: the latency variant for small batches (few warps per SM, nothing to hide latency with): the forward
 // sweep is straight-line code -- no votes, no rare-path branches -- and is simply run again with the exact
 // rules in the rare case that some lane needed one.
-template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE, bool LAT = false>
+template <int HT, int NOT_, int LT, bool PRECISE, bool UPDATE, int LAT = 0>
 __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                               float th0, float sn0, float cs0, const float *oth, int P,
                                               Traj<HT> &u, float *ga_out, float *gw_out) {
@@ -650,9 +659,9 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
     float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
     float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
     bool flag = false;
-    if (LAT && !PRECISE) {
-        forward_sweep<HT, NOT_, LT, PRECISE, 1>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, sd, gx, gy, gv,
-                                                gth, flag);
+    if (LAT != 0 && !PRECISE) {
+        forward_sweep<HT, NOT_, LT, PRECISE, 1, (LAT == 2 && NOT_ >= 3)>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc,
+                                                                         ss, sd, gx, gy, gv, gth, flag);
         if (__any_sync(OCD_FULL, flag))
             forward_sweep<HT, NOT_, LT, PRECISE, 0>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, sd, gx, gy,
                                                     gv, gth, flag);
@@ -729,7 +738,7 @@ __device__ __forceinline__ void init_start(const KParams &k, int s, float cur_sp
 }
 
 // The complete solve for one (problem, start): n_iter SGD iterations, then the final loss.
-template <int HT, int NOT_, int LT, bool PRECISE, bool LAT = false>
+template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
 __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, const float *wraw, int ws,
                                              float x0, float y0, float v0, float th0, const float *oth, int P,
                                              Traj<HT> &u) {
@@ -851,7 +860,7 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 // [H][2] and checkpoints [nseg][4] live in shared memory, thread index fastest.
 // ---------------------------------------------------------------------------------------------
 // Forward half of pass 2 of one segment: from the segment's start state, with the feature gradients.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int VM>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int VM, bool SF = false>
 __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, float x, float y, float v, float th,
                                             const float *os, int ostep, int P, const float *us, int rem, float tbase,
                                             float *ua, float *uw, float *sv, float *sc, float *ss, float *sd, float *gx,
@@ -861,6 +870,11 @@ __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, fl
     const float *ot = os;
 #pragma unroll
     for (int i = 0; i < SEG; ++i, ot += ostep) {
+        if (SF) {                                  // step fence, see forward_sweep
+            int one;
+            asm volatile("mov.u32 %0, 1;" : "=r"(one));
+            if (one == 0) continue;
+        }
         if (FULL || i < rem) {
             const float2 uu = *reinterpret_cast<const float2 *>(us + 2 * i);
             ua[i] = uu.x;
@@ -885,15 +899,18 @@ __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, fl
 // Pass 2 of one segment: the forward half above, then the reverse sweep with the SGD update.  FULL: all SEG
 // steps exist (no per-step predicates); otherwise the first `rem`.  LAT (small batches, FAST): the forward half
 // runs straight-line (vote mode 1) and is repeated with the exact rules if a lane asked for one.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, bool LAT>
+// Step fences in the segmented wide form: measured, they help with two or more other cars (H=15, 6 cars: 8.40 ->
+// 7.65 ms) and cost with one (4.74 -> 4.84 ms), so they follow the car count.
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int LAT>
 __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
                                           const float *os, int ostep, int P, float *us, int rem, float tbase,
                                           float (&lam)[4]) {
     float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
     bool flag = false;
-    if (LAT && !PRECISE) {
-        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 1>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv, sc,
-                                                          ss, sd, gx, gy, gv, gth, flag);
+    if (LAT != 0 && !PRECISE) {
+        constexpr bool SF = LAT == 2 && NOT_ != 1;
+        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 1, SF>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv,
+                                                              sc, ss, sd, gx, gy, gv, gth, flag);
         if (__any_sync(OCD_FULL, flag))
             seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv,
                                                               sc, ss, sd, gx, gy, gv, gth, flag);
@@ -931,7 +948,7 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
     lam[0] = lx; lam[1] = ly; lam[2] = lv; lam[3] = lth;
 }
 
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool LAT = false>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0>
 __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                   float th0, const float *oth, int P, const SmemTraj &u, float *ck) {
     const int H = k.H;
@@ -990,7 +1007,7 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
 }
 
 // The complete segmented solve for one (problem, start): start controls, n_iter iterations, final loss.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool LAT = false>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0>
 __device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &w, const float *wraw, int ws,
                                                  float x0, float y0, float v0, float th0, const float *oth, int P,
                                                  int s, float cur_speed, const SmemTraj &u, float *ck) {

@@ -202,13 +202,13 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     if (SEGK) {
         float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
         loss = (!PRECISE && lin)
-                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                               m.oth + p, P, s, speed, us, ck)
-                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                           m.oth + p, P, s, speed, us, ck);
     } else {
         init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
-        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
+        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
                                                                       u);
     }
     m.loss[s * P + p] = loss;
@@ -327,7 +327,7 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
                                                                          m.oth + p, P, s, v0, us, ck);
         } else {
             init_start<(HT > 0 ? HT : 1)>(k, s, v0, u);
-            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT != 0>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+            loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                            m.oth + p, P, u);
         }
         m.loss[s * P + p] = loss;
@@ -586,9 +586,11 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
 //    bench shape, 6.29 vs 6.84 ms with three cars) and every segmented kernel (H = 15: 4.74 vs 5.88 ms at 2.6*10^5
 //    problems; H = 50: 4.37 vs 5.99 ms at 6.5*10^4).  Without the votes a horizon step is one basic block and the
 //    scheduler overlaps the steps; that is worth more than the throughput form's extra warps and skipped blocks;
-//  * throughput form: compile-time horizons with four or more cars (the wide form's spills cost more than it
-//    gains: 11.0 vs 9.57 ms with six cars), whole episodes beyond 8 192 warps (one other car) / 4 096 warps,
-//    PRECISE math, and when forced.
+//  * compile-time horizons with four or more cars: the wide form with a step fence (forward_sweep's SF) above
+//    10 240 warps (8.45 vs 9.57 ms with six cars at 2^20 problems, 2.17 vs 2.50 ms at 2.6*10^5; it loses at
+//    6.5*10^4), throughput form below;
+//  * throughput form: whole episodes beyond 8 192 warps (one other car) / 4 096 warps, PRECISE math, and when
+//    forced.
 // OCD_KERNEL_FORM=throughput|latency|wide|tp overrides the choice (tests and tuning; read at every launch).
 enum { kFormAuto = 0, kFormThroughput, kFormLatency, kFormTp, kFormWide };
 inline int forced_form() {
@@ -603,7 +605,8 @@ inline bool tiny_batch(long long B, int S) {
     return f ? f == kFormTp : batch_warps(B, kTP, S) <= 800;
 }
 // -> 0 throughput, 1 latency, 2 wide.
-inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode) {
+inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode,
+                     bool many_cars_fixed_h = false) {
     const int f = forced_form();
     if (f == kFormThroughput || !has_lat) return 0;
     if (f == kFormLatency) return 1;
@@ -612,6 +615,7 @@ inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, boo
     if (w <= (one_other ? 2048 : 4096)) return 1;
     if (!has_wide) return 0;
     if (episode) return (one_other && w <= 8192) ? 2 : 0;
+    if (many_cars_fixed_h && w <= 10240) return 0;     // step-fenced wide form: three warps per sub-partition need big batches
     return 2;
 }
 
@@ -628,9 +632,9 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
         }
     }
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
-    constexpr bool HAS_WIDE = (HAS_LAT && NOT_ <= 2) || SEG_LAT;
+    constexpr bool HAS_WIDE = HAS_LAT || SEG_LAT;
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, HT > 0 && NOT_ == 1, false);
+    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, HT > 0 && NOT_ == 1, false, HT > 0 && NOT_ >= 3);
     if (form == 1) kern = k_solve<HT, NOT_, LT, PRECISE, (HAS_LAT || SEG_LAT) ? 1 : 0>;
     if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);

@@ -513,8 +513,9 @@ def test_kernel_forms_agree(engine, monkeypatch):
     (vote-guarded).  The same problems must get the same answer whichever runs: each form is forced through
     OCD_KERNEL_FORM on the same 3 000 problems, and the automatic choice is checked at three batch sizes.
     Covers the finite_horizon shape, the replanning shape (two other cars, two lanes), H = 6, the six-start set,
-    many cars, and the segmented kernels (H = 12, 15: throughput and latency forms, which fuse multiply-adds
-    differently -- same plans to tolerance, up to ill-conditioned problems)."""
+    many cars, and the segmented kernels (H = 12, 15).  Forms whose basic blocks differ (the segmented forms, the
+    step-fenced wide form for four and more cars) fuse multiply-adds differently: same plans to tolerance, up to
+    ill-conditioned problems; all other forms are bit-identical."""
     stats, ok = [], True
     for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
@@ -544,8 +545,11 @@ def test_kernel_forms_agree(engine, monkeypatch):
             same = (ref["all_plans"][:k] == res["all_plans"][:k]).flatten(1).all(dim=1)
             close = (ref["plan"][:k] - res["plan"][:k]).abs().amax(dim=(1, 2)) <= 1e-3
             stats.append((C, H, extra, name, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
-            if H <= 8:      # the register-resident forms are bit-identical
+            fenced = name == "wide" and C >= 4       # step-fenced wide form: other basic blocks, other FMA fusion
+            if H <= 8 and not fenced:                # the register-resident forms are bit-identical
                 good = same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
+            elif H <= 8:
+                good = close.float().mean().item() >= 0.995
             else:
                 good = close.float().mean().item() >= 0.98
             good = good and torch.equal(ref["best"][:k][same], res["best"][:k][same])
