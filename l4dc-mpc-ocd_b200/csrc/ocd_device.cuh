@@ -323,13 +323,14 @@ __device__ __forceinline__ float lane_min_offset(const KParams &k, float x, bool
 // VM = 1 (FAST only): no warp votes and no rare-path branches -- every block below is computed
 // unconditionally (the clamped formulations make that safe), so the whole horizon is one basic block the
 // scheduler can interleave; whatever needs an exact rule (lane tie, collision tie) raises `flag` instead.
-// RAWG (time-parallel kernels): return the FACTORS of three of the gradient components instead of the
-// products -- gv := ke (d/dv = ke sin th), gth := unused, gy := hy (d/dy = wcy hy) -- because the consumer
-// there sits behind a warp shuffle and must form the same fused multiply-adds (ke*sn + lv, ...) that the
-// compiler contracts in the single-thread kernels, or the two kernel families would round differently.
+// RAWG (every FAST kernel): return the FACTORS of three of the gradient components instead of the products --
+// gv := ke (d/dv = ke sin th), gth := unused, gy := hy (d/dy = wcy hy).  The consumer adds each of them to an
+// adjoint, and whether the compiler fuses that product and sum into one FMA depends on where the basic-block
+// boundaries of the kernel form at hand fall (and is impossible behind the time-parallel kernels' shuffles): with
+// the factors handed over, every form writes the same explicit fmaf and rounds the same way.
 // FOLD: use the per-lane folded constants of GradW for the lane term (the register-resident kernels; the
 // segmented kernels are short of registers and keep the three-instruction form).
-template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0, bool RAWG = false, bool FOLD = !LIN>
+template <int NOT_, int LT, bool PRECISE, bool LIN = false, int VM = 0, bool RAWG = !PRECISE, bool FOLD = !LIN>
 __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, float x, float y, float v,
                                              float sn, float cs, const float *oth, int jstride, int cstride,
                                              float &gx, float &gy, float &gv, float &gth, float tf, bool &flag) {
@@ -645,6 +646,7 @@ __device__ __forceinline__ void forward_sweep(const KParams &k, const GradW &w, 
         feature_grad<NOT_, LT, PRECISE, false, VM>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P,
                                                    gx[t], gy[t], gv[t], gth[t], 0.0f, flag);
     }
+    sv[H] = v; sc[H] = cs; ss[H] = sn;          // the state after the last step (sv/sc/ss[t] = before step t)
 }
 
 // LAT: the latency variant for small batches (few warps per SM, nothing to hide latency with): the forward
@@ -656,8 +658,8 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
                                               Traj<HT> &u, float *ga_out, float *gw_out) {
     constexpr int HM = Traj<HT>::HM;
     const int H = HT > 0 ? HT : k.H;
-    float sv[HM], sc[HM], ss[HM], sd[HM];      // saved v_t, cos th_t, sin th_t, d_t
-    float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1}
+    float sv[HM + 1], sc[HM + 1], ss[HM + 1], sd[HM];   // saved v_t, cos th_t, sin th_t (t = 0..H), d_t
+    float gx[HM], gy[HM], gv[HM], gth[HM];     // feature gradient at s_{t+1} (FAST: gy, gv hold factors, see RAWG)
     bool flag = false;
     if (LAT != 0 && !PRECISE) {
         forward_sweep<HT, NOT_, LT, PRECISE, 1, (LAT == 2 && NOT_ >= 3)>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc,
@@ -675,7 +677,10 @@ __device__ __forceinline__ void sgd_iteration(const KParams &k, const GradW &w, 
 #pragma unroll(HT > 0 ? HT : 1)
     for (int tt = 0; tt < H; ++tt) {
         const int t = H - 1 - tt;
-        const float mx = gx[t] + lx, my = gy[t] + ly, mv = gv[t] + lv, mth = gth[t] + lth;
+        const float mx = gx[t] + lx;
+        const float my = PRECISE ? gy[t] + ly : fmaf(w.wcy, gy[t], ly);
+        const float mv = PRECISE ? gv[t] + lv : fmaf(gv[t], ss[t + 1], lv);
+        const float mth = PRECISE ? gth[t] + lth : fmaf(__fmul_rn(gv[t], sv[t + 1]), sc[t + 1], lth);
         const float ld = fmaf(sc[t], mx, ss[t] * my);
         const float a = u.ua[t], om = u.uw[t];
         const bool in_a = (a >= -8.0f) && (a <= 4.0f);      // d clip / d a, inclusive (TF masks)
@@ -805,10 +810,10 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
         sv[HT] = v; sc[HT] = cs; ss[HT] = sn;
         float gx, hy, ke, unused;
         bool flag = false;
-        feature_grad<NOT_, LT, false, false, 1, true>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke, unused,
+        feature_grad<NOT_, LT, false, false, 1>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke, unused,
                                                       0.0f, flag);
         if (__any_sync(OCD_FULL, flag))                  // rare: a lane needs an exact tie rule
-            feature_grad<NOT_, LT, false, false, 0, true>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke,
+            feature_grad<NOT_, LT, false, false, 0>(k, w, mx_, my_, mv_, msn, mcs, omine, 2 * P, P, gx, hy, ke,
                                                           unused, 0.0f, flag);
         float GX[HT], HY[HT], KE[HT];
 #pragma unroll
@@ -889,9 +894,10 @@ __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, fl
             v = fmaf(total, k.dt, v);
             th = fmaf(oc, k.dt, th);
             Mth<PRECISE>::sincos_(th, sn, cs);
-            feature_grad<NOT_, LT, PRECISE, LIN, VM, false, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
+            feature_grad<NOT_, LT, PRECISE, LIN, VM, !PRECISE, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
                                                                    gx[i], gy[i], gv[i], gth[i], tbase + (float)(i + 1),
                                                                    flag);
+            sv[i + 1] = v; sc[i + 1] = cs; ss[i + 1] = sn;      // the state after step i (overwritten by step i+1's own save)
         }
     }
 }
@@ -905,7 +911,7 @@ template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int LAT>
 __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
                                           const float *os, int ostep, int P, float *us, int rem, float tbase,
                                           float (&lam)[4]) {
-    float ua[SEG], uw[SEG], sv[SEG], sc[SEG], ss[SEG], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
+    float ua[SEG], uw[SEG], sv[SEG + 1], sc[SEG + 1], ss[SEG + 1], sd[SEG], gx[SEG], gy[SEG], gv[SEG], gth[SEG];
     bool flag = false;
     if (LAT != 0 && !PRECISE) {
         constexpr bool SF = LAT == 2 && NOT_ != 1;
@@ -925,7 +931,10 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
     for (int ii = 0; ii < SEG; ++ii) {
         const int i = SEG - 1 - ii;
         if (FULL || i < rem) {
-            const float mx = gx[i] + lx, my = gy[i] + ly, mv = gv[i] + lv, mth = gth[i] + lth;
+            const float mx = gx[i] + lx;
+            const float my = PRECISE ? gy[i] + ly : fmaf(w.wcy, gy[i], ly);
+            const float mv = PRECISE ? gv[i] + lv : fmaf(gv[i], ss[i + 1], lv);
+            const float mth = PRECISE ? gth[i] + lth : fmaf(__fmul_rn(gv[i], sv[i + 1]), sc[i + 1], lth);
             const float ld = fmaf(sc[i], mx, ss[i] * my);
             const float a = ua[i], om = uw[i];
             const bool in_a = (a >= -8.0f) && (a <= 4.0f);

@@ -545,13 +545,9 @@ def test_kernel_forms_agree(engine, monkeypatch):
             same = (ref["all_plans"][:k] == res["all_plans"][:k]).flatten(1).all(dim=1)
             close = (ref["plan"][:k] - res["plan"][:k]).abs().amax(dim=(1, 2)) <= 1e-3
             stats.append((C, H, extra, name, round(same.float().mean().item(), 4), round(close.float().mean().item(), 4)))
-            fenced = name == "wide" and C >= 4       # step-fenced wide form: other basic blocks, other FMA fusion
-            if H <= 8 and not fenced:                # the register-resident forms are bit-identical
-                good = same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
-            elif H <= 8:
-                good = close.float().mean().item() >= 0.995
-            else:
-                good = close.float().mean().item() >= 0.98
+            # every product-plus-adjoint of the reverse sweep is an explicit fmaf (feature_grad's RAWG), so the forms
+            # round alike whatever their basic blocks: bit-identical, segmented kernels included
+            good = same.float().mean().item() >= 0.999 and close.float().mean().item() >= 0.995
             good = good and torch.equal(ref["best"][:k][same], res["best"][:k][same])
             good = good and torch.equal(ref["losses"][:k][same], res["losses"][:k][same])
             if not good:
