@@ -128,6 +128,15 @@ int ocd_reward_grad_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
                           float *reward /*[B]*/, float *grad /*[H][2][B] or NULL*/,
                           int64_t B, void *stream);
 
+/* Which form of the planner kernel a batch of B problems (episode != 0: B worlds of ocd_episode_batch) would run:
+ * the throughput form (warp votes skip inactive feature blocks), the latency form (straight-line sweep, for small
+ * batches), the wide form (the same under a register cap, for large batches) or the time-parallel form (eight
+ * lanes per start, for the smallest).  All forms give bit-identical results; the choice follows measurements on
+ * B200 and can be forced with the environment variable OCD_KERNEL_FORM=throughput|latency|wide|tp.
+ * Pure host logic (no CUDA call).  -> OCD_FORM_* or a negative status. */
+enum { OCD_FORM_THROUGHPUT = 0, OCD_FORM_LATENCY = 1, OCD_FORM_WIDE = 2, OCD_FORM_TIME_PARALLEL = 3 };
+int ocd_kernel_form(const ocd_params *p, int64_t B, int episode);
+
 /* Jacobian of the horizon-summed features with respect to the controls: what the reference's inverse
  * optimal control classes take from tf.GradientTape -- segment_loss's d r / d u = J^T w
  * (interact_drive/reward_design/first_order_ioc.py:62-91) and segment_jacobian / total_jacobian

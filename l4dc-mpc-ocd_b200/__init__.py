@@ -6,11 +6,11 @@
 """
 from . import _native  # noqa: F401  (raises ImportError when libocd_b200.so has not been built)
 from .engine import (  # noqa: F401
-    Engine, HostContext, PlannerParams, Scenario, MATH_FAST, MATH_PRECISE, OPT_SGD, OPT_LBFGS, device_count,
+    Engine, HostContext, PlannerParams, Scenario, MATH_FAST, MATH_PRECISE, OPT_SGD, OPT_LBFGS, device_count, kernel_form,
 )
 
 __all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "OPT_SGD", "OPT_LBFGS",
-           "device_count"]
+           "device_count", "kernel_form"]
 
 
 def install_as_reference() -> None:

@@ -17,6 +17,7 @@ MAX_LANES, MAX_OTHER, MAX_PLAN, MAX_H, MAX_STARTS = 4, 7, 16, 64, 6
 LBFGS_MAX_H = 16
 OK, EINVAL, EUNSUP, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 SMOOTH_F, SMOOTH_THRESHOLD, SMOOTH_BUMP = 0, 1, 2
+FORM_THROUGHPUT, FORM_LATENCY, FORM_WIDE, FORM_TIME_PARALLEL = 0, 1, 2, 3
 
 
 class OcdError(RuntimeError):
@@ -62,6 +63,7 @@ _PROTOTYPES = {
     "ocd_smooth_batch": (C.c_int, [C.c_int, _P, C.c_double, C.c_double, _P, _I64, _P]),
     "ocd_features_batch": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ocd_reward_grad_batch": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P]),
+    "ocd_kernel_form": (C.c_int, [_P, _I64, C.c_int]),
     "ocd_feature_jacobian_batch": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ocd_solve_batch": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "ocd_episode_batch": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32,

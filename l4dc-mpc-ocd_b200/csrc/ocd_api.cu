@@ -426,6 +426,21 @@ static int launch_episode(const KParams &k, bool precise, const ocd_scenario &sc
     OCD_DISPATCH(launch_episode_t, false, k, sc, a, st);
 }
 
+// the same two dispatches, asking which kernel form would run (ocd_kernel_form)
+static int form_of(const KParams &k, bool precise, long long B, bool episode) {
+    if (precise) OCD_DISPATCH(form_t, true, k, B, episode);
+    if (!episode && k.L == 3 && k.NO >= 2 && k.NO <= 5) {
+        const bool h5 = k.H == 5;
+        switch (k.NO) {
+            case 2: return h5 ? form_t<5, 2, 3, false>(k, B, false) : form_t<0, 2, 3, false>(k, B, false);
+            case 3: return h5 ? form_t<5, 3, 3, false>(k, B, false) : form_t<0, 3, 3, false>(k, B, false);
+            case 4: return h5 ? form_t<5, 4, 3, false>(k, B, false) : form_t<0, 4, 3, false>(k, B, false);
+            default: return h5 ? form_t<5, 5, 3, false>(k, B, false) : form_t<0, 5, 3, false>(k, B, false);
+        }
+    }
+    OCD_DISPATCH(form_t, false, k, B, episode);
+}
+
 }  // namespace ocd
 
 // ---------------------------------------------------------------------------------------------
@@ -449,6 +464,15 @@ const char *ocd_strerror(int code) {
 }
 
 int ocd_num_starts(const ocd_params *p) { return (p && p->extra_inits) ? 6 : 3; }
+
+int ocd_kernel_form(const ocd_params *p, int64_t B, int episode) {
+    KParams k;
+    const int rc = digest(p, k);
+    if (rc) return rc;
+    if (B < 0) return OCD_EINVAL;
+    if (k.optimizer == 1) return episode ? (int)OCD_EUNSUP : (int)OCD_FORM_THROUGHPUT;     // k_solve_lbfgs has one form
+    return form_of(k, p->math_mode == 1, B, episode != 0);
+}
 
 int ocd_device_count(void) {
     int n = 0;

@@ -619,24 +619,34 @@ inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, boo
     return 2;
 }
 
+// The form the (HT, NOT_, LT, PRECISE) specialisation runs for B problems: 0 throughput, 1 latency, 2 wide,
+// 3 time-parallel.  One function for both launchers and for ocd_kernel_form.
+template <int HT, int NOT_, int LT, bool PRECISE>
+inline int choose_form(const KParams &k, long long B, bool episode) {
+    constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;          // compile-time horizon and car count
+    constexpr bool SEG_LAT = HT == 0 && !PRECISE;                       // segmented kernels (solve only)
+    if (HAS_LAT && HT <= kTG && tiny_batch(B, k.S)) return 3;
+    if (episode) return pick_form(B, kP, k.S, HAS_LAT, HAS_LAT && NOT_ == 1, NOT_ == 1, true);
+    return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, HT > 0 && NOT_ == 1, false, HT > 0 && NOT_ >= 3);
+}
+
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
+    constexpr bool ANY_LAT = HAS_LAT || (HT == 0 && !PRECISE);
+    const int form = choose_form<HT, NOT_, LT, PRECISE>(k, a.B, false);
     if constexpr (HAS_LAT && HT <= kTG) {
-        if (tiny_batch(a.B, k.S)) {
+        if (form == 3) {
             const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, false, false, false) * sizeof(float);
             k_solve_tp<HT, NOT_, LT><<<(unsigned)((a.B + kTP - 1) / kTP), k.S * kTP * kTG, tb, st>>>(k, a);
             return cuda_status();
         }
     }
-    constexpr bool SEG_LAT = HT == 0 && !PRECISE;      // runtime horizons: latency variant of the segmented kernel
-    constexpr bool HAS_WIDE = HAS_LAT || SEG_LAT;
     auto kern = k_solve<HT, NOT_, LT, PRECISE>;
-    const int form = pick_form(a.B, a.P, k.S, HAS_LAT || SEG_LAT, HAS_WIDE, HT > 0 && NOT_ == 1, false, HT > 0 && NOT_ >= 3);
-    if (form == 1) kern = k_solve<HT, NOT_, LT, PRECISE, (HAS_LAT || SEG_LAT) ? 1 : 0>;
-    if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
+    if (form == 1) kern = k_solve<HT, NOT_, LT, PRECISE, ANY_LAT ? 1 : 0>;
+    if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, ANY_LAT ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
@@ -649,16 +659,16 @@ int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, true, HT == 0,
                                      slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
+    constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
+    const int form = choose_form<HT, NOT_, LT, PRECISE>(k, a.B, true);
     if constexpr (HAS_LAT && HT <= kTG) {
-        if (tiny_batch(a.B, k.S)) {
+        if (form == 3) {
             const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, true, false, false) * sizeof(float);
             k_episode_tp<HT, NOT_, LT><<<(unsigned)((a.B + kTP - 1) / kTP), k.S * kTP * kTG, tb, st>>>(k, sc, a);
             return cuda_status();
         }
     }
     auto kern = k_episode<HT, NOT_, LT, PRECISE>;
-    constexpr bool HAS_WIDE = HAS_LAT && NOT_ == 1;
-    const int form = pick_form(a.B, a.P, k.S, HAS_LAT, HAS_WIDE, NOT_ == 1, true);
     if (form == 1) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_LAT ? 1 : 0>;
     if (form == 2) kern = k_episode<HT, NOT_, LT, PRECISE, HAS_WIDE ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
@@ -667,5 +677,9 @@ int launch_episode_t(const KParams &k, const ocd_scenario &sc, const EpisodeArgs
     kern<<<grid, k.S * a.P, bytes, st>>>(k, sc, a);
     return cuda_status();
 }
+
+// choose_form behind the launchers' signature, so that the same dispatch macro can ask for it
+template <int HT, int NOT_, int LT, bool PRECISE>
+int form_t(const KParams &k, long long B, bool episode) { return choose_form<HT, NOT_, LT, PRECISE>(k, B, episode); }
 
 }  // namespace ocd

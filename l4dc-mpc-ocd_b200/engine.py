@@ -110,6 +110,20 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+FORM_NAMES = {N.FORM_THROUGHPUT: "throughput", N.FORM_LATENCY: "latency", N.FORM_WIDE: "wide",
+              N.FORM_TIME_PARALLEL: "time-parallel"}
+
+
+def kernel_form(p: "PlannerParams", B: int, episode: bool = False) -> str:
+    """Which form of the planner kernel a batch of B problems (or B episode worlds) would run -- host logic, needs
+    no GPU (`ocd_kernel_form`)."""
+    ps = p.c_struct()
+    rc = N.lib.ocd_kernel_form(C.addressof(ps), int(B), int(bool(episode)))
+    if rc < 0:
+        N.check(rc, "ocd_kernel_form")
+    return FORM_NAMES[rc]
+
+
 def device_count() -> int:
     return int(N.lib.ocd_device_count())
 

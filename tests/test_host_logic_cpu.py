@@ -223,3 +223,32 @@ def test_first_order_ioc_host_math():
     assert abs(abs(F.l2_normalize(theta) @ w) - 1) < 1e-6
     assert F.gradient_norm_loss(w, [A]) < 1e-20 < F.gradient_norm_loss(F.l2_normalize(np.ones(7)), [A])
     assert abs(np.linalg.norm(F.l2_normalize(np.zeros(3) + 1e-30))) <= 1.0
+
+
+def test_kernel_form_selection(monkeypatch):
+    """ocd_kernel_form is host logic: which kernel form a batch would run ("Form selection")."""
+    import l4dc_mpc_ocd_b200 as ocd
+    monkeypatch.delenv("OCD_KERNEL_FORM", raising=False)
+    fh = ocd.PlannerParams()                                            # H=5, one other car: the bench shape
+    assert [ocd.kernel_form(fh, B) for B in (1, 45, 1000, 1100, 20000, 30000, 1 << 20)] == \
+        ["time-parallel", "time-parallel", "time-parallel", "latency", "latency", "wide", "wide"]
+    assert [ocd.kernel_form(fh, B, episode=True) for B in (45, 5000, 60000, 100000)] == \
+        ["time-parallel", "latency", "wide", "throughput"]
+    rp = ocd.PlannerParams(C=3, lane_x=(-0.05, 0.05), num_lanes=2)      # replanning: two other cars
+    assert [ocd.kernel_form(rp, B) for B in (180, 40000, 1 << 20)] == ["time-parallel", "latency", "wide"]
+    assert ocd.kernel_form(rp, 100000, episode=True) == "throughput"
+    six = ocd.PlannerParams(C=6)                                        # step-fenced wide form: big batches only
+    assert [ocd.kernel_form(six, B) for B in (500, 30000, 65536, 262144)] == \
+        ["time-parallel", "latency", "throughput", "wide"]
+    assert [ocd.kernel_form(ocd.PlannerParams(H=15), B) for B in (100, 40000, 1 << 20)] == ["latency", "latency", "wide"]
+    assert ocd.kernel_form(ocd.PlannerParams(H=50, C=6), 65536) == "wide"
+    assert ocd.kernel_form(ocd.PlannerParams(H=15), 1000, episode=True) == "throughput"     # segmented episodes: one form
+    assert ocd.kernel_form(ocd.PlannerParams(math_mode=ocd.MATH_PRECISE), 100) == "throughput"
+    assert ocd.kernel_form(ocd.PlannerParams(optimizer=ocd.OPT_LBFGS), 100) == "throughput"
+    for form, want in (("throughput", "throughput"), ("latency", "latency"), ("wide", "wide"), ("tp", "time-parallel")):
+        monkeypatch.setenv("OCD_KERNEL_FORM", form)
+        assert ocd.kernel_form(fh, 4096) == want
+    monkeypatch.setenv("OCD_KERNEL_FORM", "tp")
+    assert ocd.kernel_form(ocd.PlannerParams(H=15), 4096) == "latency"   # no time-parallel form above H = 8: falls back
+    with pytest.raises(ValueError):
+        ocd.kernel_form(ocd.PlannerParams(H=65), 10)
