@@ -31,12 +31,13 @@ namespace ocd {
 // instead of six at the 76-80 the code would like; the 24 bytes of spill that costs are paid back by the extra
 // warp (5.09 -> 4.97 ms at the bench shape; 64 registers / eight warps measured no better).  The segmented
 // throughput kernels get 96 registers (five warps per sub-partition).  The latency form takes what it needs
-// (140-250).  The wide form is the same straight-line code held to 128 registers with one other car (four warps
-// per sub-partition) and 168 with more (three): measured against 112 / 128 / 168 on every shape of the sweep
+// (140-250).  The wide form is the same straight-line code held to 128 registers (four warps per sub-partition)
+// with one other car, and with three at a compile-time horizon (which would otherwise settle just above 128), and
+// to 168 (three warps) elsewhere: measured against 112 / 128 / 168 on every shape of the sweep
 // (scratch/wide_regs.sh); it is the fastest form for large batches of most shapes (see pick_form).
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? ((NOT_) == 1 ? 128 : 168) : ((HT) > 0 ? 72 : 96)))
+    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96)))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 

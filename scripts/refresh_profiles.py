@@ -42,7 +42,7 @@ def summ(rep, out, title):
 
 main = summ(G / f"prof_solve_{tag}.ncu-rep", P / "r01_k_solve_ncu_summary.txt",
             "k_solve<5,1,3,fast,wide> at the bench shape (B = 2^20, H=5, 2 cars)")
-for name, title in (("h5c6", "k_solve<5,5,3,fast>: sweep point H=5, 6 cars, B = 262144"),
+for name, title in (("h5c6", "k_solve<5,5,3,fast,wide+step fence>: sweep point H=5, 6 cars, B = 262144"),
                     ("h15c2", "k_solve<0,1,3,fast,wide> (segmented adjoint): sweep point H=15, 2 cars, B = 262144"),
                     ("h50c2", "k_solve<0,1,3,fast,wide> (segmented adjoint): sweep point H=50, 2 cars, B = 65536")):
     rep = G / f"prof_{tag}_{name}.ncu-rep"
