@@ -418,11 +418,7 @@ class HostContext:
         calls skip their staging copies (pageable arrays work too, through a pinned staging area)."""
         t = torch.empty(tuple(shape), dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.int32,
                         pin_memory=True)
-        a = t.numpy()
-        HostContext._keepalive[a.ctypes.data] = t
-        return a
-
-    _keepalive: dict = {}
+        return t.numpy()          # the array keeps the pinned storage alive (ndarray.base), and frees it with itself
 
     def solve_soa(self, p: PlannerParams, world: np.ndarray, weights: np.ndarray, weight_idx=None,
                   other_controls=None, cur_speed=None, out=None):
