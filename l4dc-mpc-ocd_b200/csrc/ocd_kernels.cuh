@@ -34,7 +34,7 @@ namespace ocd {
 // (140-250).  The wide form is the same straight-line code held to 128 registers (four warps per sub-partition)
 // with one other car, and with three at a compile-time horizon (which would otherwise settle just above 128), and
 // to 168 (three warps) elsewhere: measured against 112 / 128 / 168 on every shape of the sweep
-// (scratch/wide_regs.sh); it is the fastest form for large batches of most shapes (see pick_form).
+// (scripts/tuning/wide_regs.sh); it is the fastest form for large batches of most shapes (see pick_form).
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
     __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96)))
@@ -577,7 +577,7 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
     return OCD_OK;
 }
 
-// Which form runs (measured on B200, scratch/form_sweep*.py, scratch/form_ep.py, scratch/wide_regs.sh; times in
+// Which form runs (measured on B200, scripts/tuning/form_sweep*.py, form_ep.py, wide_regs.sh; times in
 // DESIGN.md):
 //  * time-parallel: up to ~800 warps of 4 starts (about 1 000 problems) -- below that its shorter dependent chain
 //    wins, above it its 4x instruction count per solve loses;
