@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -623,6 +627,10 @@ int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc, const float *
 static constexpr int kCtxStreams = 4;     // H2D, two compute lanes, D2H
 static constexpr int kMaxChunks = 16;
 
+struct CopyPool;
+static CopyPool *copy_pool_new();
+static void copy_pool_free(CopyPool *);
+
 struct ocd_ctx {
     int device;
     cudaStream_t stream;                 // small calls (episodes)
@@ -632,6 +640,7 @@ struct ocd_ctx {
     cudaEvent_t done[kMaxChunks];        // chunk c's outputs are in host memory
     char *dev;      size_t dev_cap;
     char *pin;      size_t pin_cap;
+    CopyPool *pool;                      // staging-copy workers (created on the first large copy)
 };
 
 static int ctx_reserve(ocd_ctx *c, size_t dev_bytes, size_t pin_bytes) {
@@ -658,6 +667,7 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
     ocd_ctx *c = new (std::nothrow) ocd_ctx();
     if (!c) return OCD_ENOMEM;
     c->device = device;
+    c->pool = copy_pool_new();
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < kCtxStreams; ++i)
         ok = ok && cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -667,6 +677,7 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
              cudaEventCreateWithFlags(&c->solved[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
+        copy_pool_free(c->pool);
         delete c;
         return OCD_ECUDA;
     }
@@ -677,6 +688,7 @@ int ocd_ctx_create(int device, ocd_ctx **out) {
 void ocd_ctx_destroy(ocd_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    copy_pool_free(c->pool);
     if (c->dev) cudaFree(c->dev);
     if (c->pin) cudaFreeHost(c->pin);
     cudaStreamDestroy(c->stream);
@@ -751,45 +763,113 @@ static int chunk_schedule(int64_t B, int64_t *start) {
     return m;
 }
 
-// Staging copies between pageable user arrays and the context's pinned area: `rows` row segments of
-// `bytes` bytes each.  One core moves ~10 GB/s, far less than the PCIe link, so copies above 1 MiB are
-// split over a few short-lived threads (by bytes, not by rows: a chunk has as few as one row).
-static void copy_rows(char *dst, size_t dst_stride, const char *src, size_t src_stride, int rows, size_t bytes) {
-    const size_t total = (size_t)rows * bytes;
-    unsigned nt = 1;
-    if (total >= (1u << 20)) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        nt = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
-        const unsigned by_size = (unsigned)(total >> 19);          // at least 512 KiB per thread
-        if (nt > by_size) nt = by_size;
-    }
-    auto span = [=](size_t lo, size_t hi) {                         // bytes [lo, hi) of the rows laid end to end
+// Staging copies between pageable user arrays and the context's pinned area: `rows` row segments of `bytes`
+// bytes each.  One core moves ~10 GB/s, far less than the PCIe link, so copies above 1 MiB are cut into slices
+// (by bytes, not by rows: a chunk has as few as one row) that the context's worker threads and the caller take
+// from a shared counter.  The workers are created once per context, on the first large copy: a thread per copy
+// cost more than the copy (a 2^20-problem call makes ~40 such copies).
+struct CopyJob {
+    char *dst; const char *src;
+    size_t dst_stride, src_stride, bytes, total, slice, nslices;
+    std::atomic<size_t> next{0}, done{0};
+    void span(size_t lo, size_t hi) const {                   // bytes [lo, hi) of the rows laid end to end
         while (lo < hi) {
             const size_t r = lo / bytes, off = lo % bytes;
             const size_t len = (bytes - off < hi - lo) ? bytes - off : hi - lo;
             std::memcpy(dst + r * dst_stride + off, src + r * src_stride + off, len);
             lo += len;
         }
-    };
-    if (nt <= 1) {
-        span(0, total);
+    }
+    void work() {                                             // take slices until none is left
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nslices) return;
+            const size_t lo = i * slice, hi = lo + slice < total ? lo + slice : total;
+            span(lo, hi);
+            done.fetch_add(1);
+        }
+    }
+};
+
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv;
+    std::shared_ptr<CopyJob> job;       // the current job; a late worker keeps its (exhausted) job alive on its own
+    uint64_t gen = 0;
+    bool stop = false;
+
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::shared_ptr<CopyJob> j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                j = job;
+            }
+            if (j) j->work();
+        }
+    }
+    bool start(unsigned n) {            // false: no workers (the caller copies alone)
+        if (!workers.empty()) return true;
+        try {
+            workers.reserve(n);
+            for (unsigned i = 0; i < n; ++i) workers.emplace_back([this] { run(); });
+        } catch (...) {
+        }
+        return !workers.empty();
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (std::thread &t : workers) t.join();
+        workers.clear();
+    }
+};
+
+static CopyPool *copy_pool_new() { return new (std::nothrow) CopyPool(); }
+static void copy_pool_free(CopyPool *p) {
+    if (!p) return;
+    p->shutdown();
+    delete p;
+}
+
+static void copy_rows(CopyPool *pool, char *dst, size_t dst_stride, const char *src, size_t src_stride, int rows,
+                      size_t bytes) {
+    const size_t total = (size_t)rows * bytes;
+    CopyJob local{dst, src, dst_stride, src_stride, bytes, total, total, 1};
+    if (!pool || total < (1u << 20)) {
+        local.span(0, total);
         return;
     }
-    const size_t per = ((total + nt - 1) / nt + 63) & ~(size_t)63;
-    std::vector<std::thread> pool;
-    size_t handed = per < total ? per : total;             // bytes [0, handed) are this thread's share
-    try {                                                   // nothing may throw across the C ABI: whatever
-        pool.reserve(nt - 1);                               // could not be handed to a thread is copied here
-        for (unsigned t = 1; t < nt && handed < total; ++t) {
-            const size_t lo = handed, hi = lo + per < total ? lo + per : total;
-            pool.emplace_back(span, lo, hi);
-            handed = hi;
-        }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nw = hw >= 16 ? 7 : (hw >= 4 ? hw / 2 - 1 : 0);          // workers beside the caller
+    std::shared_ptr<CopyJob> j;
+    try {                                                                     // nothing may throw across the C ABI
+        if (nw && pool->start(nw)) j = std::make_shared<CopyJob>();
     } catch (...) {
     }
-    span(0, per < total ? per : total);
-    if (handed < total) span(handed, total);
-    for (std::thread &th : pool) th.join();
+    if (!j) {
+        local.span(0, total);
+        return;
+    }
+    j->dst = dst; j->src = src; j->dst_stride = dst_stride; j->src_stride = src_stride; j->bytes = bytes; j->total = total;
+    j->slice = (size_t)512 << 10;                                             // 512 KiB slices
+    j->nslices = (total + j->slice - 1) / j->slice;
+    {
+        std::lock_guard<std::mutex> lk(pool->m);
+        pool->job = j;
+        ++pool->gen;
+    }
+    pool->cv.notify_all();
+    j->work();
+    while (j->done.load() < j->nslices) std::this_thread::yield();           // the last slices are in flight
 }
 
 // One [rows][B] host array moved in column chunks.  Pinned user memory is copied in place (a
@@ -811,7 +891,7 @@ static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
                               cudaMemcpyHostToDevice, st);
     } else {
         char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
-        copy_rows(stage, n * a.elem, a.user + b0 * a.elem, B * a.elem, a.rows, n * a.elem);
+        copy_rows(c->pool, stage, n * a.elem, a.user + b0 * a.elem, B * a.elem, a.rows, n * a.elem);
         e = cudaMemcpyAsync(dst, stage, (size_t)a.rows * n * a.elem, cudaMemcpyHostToDevice, st);
     }
     return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
@@ -832,7 +912,7 @@ static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
 static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n) {
     if (a.pinned) return;
     const char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
-    copy_rows(a.user + b0 * a.elem, B * a.elem, stage, n * a.elem, a.rows, n * a.elem);
+    copy_rows(c->pool, a.user + b0 * a.elem, B * a.elem, stage, n * a.elem, a.rows, n * a.elem);
 }
 
 // The batch is cut into column chunks that flow through four streams linked by per-chunk events: one
@@ -881,7 +961,7 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     const size_t o_w = dev.take(n_w), s_w = pin.take(pin_w ? 0 : n_w);
     const size_t o_oc = dev.take(n_oc), s_oc = pin.take(pin_oc ? 0 : n_oc);
     if ((rc = ctx_reserve(c, dev.off, pin.off))) return rc;
-    if (n_w && !pin_w) copy_rows(c->pin + s_w, n_w, (const char *)weights, n_w, 1, n_w);
+    if (n_w && !pin_w) copy_rows(c->pool, c->pin + s_w, n_w, (const char *)weights, n_w, 1, n_w);
     if (n_oc && !pin_oc) std::memcpy(c->pin + s_oc, other_controls, n_oc);
     cudaStream_t s0 = c->lanes[0];        // the H2D stream: chunk copies are ordered behind the shared inputs
     if (n_w && cudaMemcpyAsync(c->dev + o_w, pin_w ? (const char *)weights : c->pin + s_w, n_w, cudaMemcpyHostToDevice,
