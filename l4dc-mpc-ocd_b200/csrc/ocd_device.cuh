@@ -335,6 +335,11 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                                              float sn, float cs, const float *oth, int jstride, int cstride,
                                              float &gx, float &gy, float &gv, float &gth, float tf, bool &flag) {
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
+    // ONE_RCP (register-resident kernels with one or two other cars): the collision bump and the fence each take
+    // their two reciprocals from ONE MUFU (1/a, 1/b = b R, a R with R = 1/(a b)).  The XU pipe -- 8 cycles per
+    // MUFU -- is the top stall of the straight-line forms, and three more FMULs for one MUFU less gain 2.4 % at the
+    // bench shape (4.77 -> 4.66 ms); measured, it costs 1-4 % with more cars and in the segmented kernels.
+    constexpr bool ONE_RCP = FOLD && !PRECISE && (NOT_ == 1 || NOT_ == 2);
     // speed: min((v sin th - ts)^2, 4 ts^2)                                  merging.py:58-59
     {
         const float e = fmaf(v, sn, -k.ts);
@@ -410,7 +415,16 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 const float ux = fmaf(-nx, nx, 1.0f), uy = fmaf(-ny, ny, 1.0f);
                 float val = 0.0f, vx = 0.0f, vy = 0.0f;
                 if (VM == 1 || __any_sync(OCD_FULL, fminf(ux, uy) > 0.0f)) {
-                    const float rx = Mth<false>::rcp_(fmaxf(ux, 1e-6f)), ry = Mth<false>::rcp_(fmaxf(uy, 1e-6f));
+                    const float uxc = fmaxf(ux, 1e-6f), uyc = fmaxf(uy, 1e-6f);
+                    float rx, ry;
+                    if (ONE_RCP) {                   // 1/ux and 1/uy from one MUFU
+                        const float R = Mth<false>::rcp_(uxc * uyc);
+                        rx = uyc * R;
+                        ry = uxc * R;
+                    } else {
+                        rx = Mth<false>::rcp_(uxc);
+                        ry = Mth<false>::rcp_(uyc);
+                    }
                     val = Mth<false>::ex2_(fmaf(rx + ry, -OCD_LOG2E, 2.0f * OCD_LOG2E));
                     vx = (val * nx) * (rx * rx);
                     vy = (val * ny) * (ry * ry);
@@ -508,10 +522,19 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
             // r2 = 1/(shape width - qs); dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping qs and its
             // complement to a tiny positive number makes the exponential saturate: T = 0, dT = 0 below the
             // ramp and T = 1, dT = 0 above it, so the three regions need no branch.
-            const float r1 = Mth<false>::rcp_(fmaxf(qs, 1e-7f));
-            const float r2 = Mth<false>::rcp_(fmaxf(k.fs_w - qs, 1e-7f));
-            const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_((r1 - r2) * OCD_LOG2E));
-            const float dT = (T * (1.0f - T)) * (k.fshape * fmaf(r1, r1, r2 * r2));
+            const float qc = fmaxf(qs, 1e-7f), uc = fmaxf(k.fs_w - qs, 1e-7f);
+            float z, rr;                                   // z = r1 - r2, rr = r1^2 + r2^2
+            if (ONE_RCP) {     // one reciprocal serves both: with R = 1/(q u), z = (u - q) R and rr = (u^2 + q^2) R^2
+                const float R = Mth<false>::rcp_(qc * uc);
+                z = (uc - qc) * R;
+                rr = fmaf(uc, uc, qc * qc) * (R * R);
+            } else {
+                const float r1 = Mth<false>::rcp_(qc), r2 = Mth<false>::rcp_(uc);
+                z = r1 - r2;
+                rr = fmaf(r1, r1, r2 * r2);
+            }
+            const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_(z * OCD_LOG2E));
+            const float dT = (T * (1.0f - T)) * (k.fshape * rr);
             gx = fmaf(w.wfence, copysignf(fmaf(dT, ax, T), x), gx);
         }
     }
