@@ -93,3 +93,15 @@ def test_product_never_imports_the_oracle():
                           "l4dc_mpc_ocd_b200.interact_drive.reward_design.mpc_ord, l4dc_mpc_ocd_b200.experiments.run_mpc_ord; "
                           "print('oracle' in sys.modules)" % str(ROOT)], capture_output=True, text=True, check=True)
     assert out.stdout.strip() == "False"
+
+
+def test_integration_stub_matches_the_struct():
+    """INTEGRATION.md shows the ctypes binding a maintainer of the reference would add; its ocd_params must have
+    the fields of the real struct, in order (a stale copy would silently mis-align every argument)."""
+    import l4dc_mpc_ocd_b200 as ocd
+    text = (ROOT / "INTEGRATION.md").read_text()
+    block = text[text.index("class ocd_params(C.Structure)"):]
+    block = block[:block.index("assert _lib.ocd_abi_version()")]
+    names = re.findall(r'\("(\w+)",\s*C\.c_', block)
+    assert names == [f[0] for f in ocd._native.ocd_params._fields_]
+    assert "ocd_abi_version() == %d" % ocd._native.ABI_VERSION in text
