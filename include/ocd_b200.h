@@ -21,6 +21,10 @@
  *   - Return value: 0 on success, a negative OCD_E* code otherwise (ocd_strerror()).  Nothing
  *     throws or exits across the ABI.  There is NO CPU fallback: without a CUDA device every
  *     compute entry point returns OCD_ECUDA.
+ *   - Two environment variables are read (never written) at call time, for tests and tuning:
+ *     OCD_KERNEL_FORM=throughput|latency|wide|tp forces a kernel form (see ocd_kernel_form; all forms
+ *     give bit-identical results) and OCD_HOST_CHUNKS="w0,w1,..." sets the chunk weights of
+ *     ocd_solve_batch_host's copy/compute pipeline.
  */
 #ifndef OCD_B200_H
 #define OCD_B200_H
