@@ -69,6 +69,7 @@ class MPC_ORD:
         self._device = device
         self.program = compile_world(world, car)
         self.kernel_launches = 0
+        self._dev_cache = {}
 
     # -- the batched core ------------------------------------------------------------------------------
     @staticmethod
@@ -112,16 +113,24 @@ class MPC_ORD:
                 return o["returns"]
             returns = _par.sharded_returns(run, B)
             out = dict(returns=returns, final_world=run.final)
+        elif not trace:
+            # the CMA-ES hot loop: everything but the candidates is the same from one generation to the next, so
+            # the device copies of the initial states / indices are kept, only W goes up and ONE buffer (returns +
+            # final worlds) comes back
+            ret_flat, final = self._episode_returns_cached(eng, W, robot, widx, unlucky)
+            out = None
         else:
             out = eng.episodes(self.program.params, self.program.scenario, robot, W, as_f32(self.designer_weights),
                                self.designer_horizon, weight_idx=widx, unlucky_idx=unlucky, trace=trace,
                                final_world=True)
         self.kernel_launches += 1
-        ret = out["returns"].cpu().numpy().reshape(nc, ni, ns)
+        if out is not None:
+            ret_flat = out["returns"].cpu().numpy()
+            final = out["final_world"].cpu().numpy()[-1]
+        ret = ret_flat.reshape(nc, ni, ns)
         # leave the Python objects the way a serial evaluation would: last weights, last init, final state
         self.car.weights = W[-1]
         self.car.init_state = I[-1]
-        final = out["final_world"].cpu().numpy()[-1]
         for c, s in zip(self.world.cars, final):
             c.state = s
         if trace:
@@ -129,6 +138,30 @@ class MPC_ORD:
         return ret
 
     # -- reference API -----------------------------------------------------------------------------------
+    def _episode_returns_cached(self, eng, W, robot, widx, unlucky):
+        """-> (returns [B] host, final world [C, 4] of the last episode); see episode_returns."""
+        import torch
+        p, sc = self.program.params, self.program.scenario
+        B, dev = robot.shape[0], eng.device
+        key = (robot.tobytes(), widx.tobytes(), None if unlucky is None else unlucky.tobytes(), str(dev))
+        c = self._dev_cache.get(key)
+        if c is None:
+            if len(self._dev_cache) >= 8:
+                self._dev_cache.clear()
+            c = dict(ri=torch.as_tensor(np.ascontiguousarray(robot.T), device=dev),
+                     idx=torch.as_tensor(widx, device=dev),
+                     tw=torch.as_tensor(as_f32(self.designer_weights), device=dev),
+                     ul=None if unlucky is None else torch.as_tensor(unlucky, device=dev),
+                     out=torch.empty(((1 + p.C * 4) * B,), dtype=torch.float32, device=dev))
+            self._dev_cache[key] = c
+        w = torch.as_tensor(np.ascontiguousarray(W.T), device=dev)                   # [K][n_cand]
+        buf = c["out"]
+        views = dict(returns=buf[:B], final_world=buf[B:].view(p.C, 4, B))
+        eng.episodes_soa(p, sc, c["ri"], w, W.shape[0], c["tw"], self.designer_horizon, weight_idx=c["idx"],
+                         unlucky_idx=c["ul"], final_world=True, out=views)
+        host = buf.cpu().numpy()
+        return host[:B], host[B:].reshape(p.C, 4, B)[:, :, -1]
+
     def eval_weights_for_init(self, init, weights, render=False, heatmap_show=False):
         """Return of `weights` from one initial state, summed over the samples (reference :67-106)."""
         if render:
