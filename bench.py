@@ -260,6 +260,8 @@ def main():
     nominal_tf = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved_tf / (fp32_peak / 1e12), "traffic": traffic,
+                "bound_note": "BASELINE's north_star names the FP32 pipe as this path's roofline: no stage is a dense "
+                              "contraction (no tensor roofline) and HBM carries 0.3 % of its measured bandwidth (see hbm)",
                 "peak_source": "dependent-free FFMA kernel measured in this job (MEASURED_PEAKS.json has no FP32 figure)",
                 "nominal_peak": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
                 "flops_per_solve": flops, "kernel": "k_solve<5,1,3,fast,wide>", "kernel_ms": own_ms}
