@@ -21,10 +21,12 @@
  *   - Return value: 0 on success, a negative OCD_E* code otherwise (ocd_strerror()).  Nothing
  *     throws or exits across the ABI.  There is NO CPU fallback: without a CUDA device every
  *     compute entry point returns OCD_ECUDA.
- *   - Two environment variables are read (never written) at call time, for tests and tuning:
+ *   - Environment variables read (never written) at call time, for tests and tuning:
  *     OCD_KERNEL_FORM=throughput|latency|wide|tp forces a kernel form (see ocd_kernel_form; all forms
- *     give bit-identical results) and OCD_HOST_CHUNKS="w0,w1,..." sets the chunk weights of
- *     ocd_solve_batch_host's copy/compute pipeline.
+ *     give bit-identical results); OCD_RUNTIME_H=1 runs H = 15 / 50 on the runtime-horizon kernels instead of
+ *     their compile-time specialisations; OCD_HOST_CHUNKS="w0,w1,..." sets the chunk weights of
+ *     ocd_solve_batch_host's copy/compute pipeline and OCD_HOST_THREADS=<n> its staging-copy threads (default: the
+ *     cores in the calling process's affinity mask, at most 8).
  */
 #ifndef OCD_B200_H
 #define OCD_B200_H
@@ -208,6 +210,16 @@ int ocd_solve_batch_host(ocd_ctx *ctx, const ocd_params *p, const float *world,
                          const float *weights, int64_t Bw, const int32_t *weight_idx,
                          const float *cur_speed,
                          float *plan, float *losses, int32_t *best, int64_t B);
+
+/* The same solve for a receding-horizon caller, which applies plan[0] and discards the rest
+ * (PlannerCar._get_next_control returns plan[0]: interact_drive/car/planner_car.py:80-85): only the first control
+ * [2][B] travels back (8 B per solve instead of 8 H), and losses / best are optional (NULL: not copied). */
+int ocd_solve_first_host(ocd_ctx *ctx, const ocd_params *p, const float *world,
+                         const float *other_controls, int64_t Bo,
+                         const float *weights, int64_t Bw, const int32_t *weight_idx,
+                         const float *cur_speed,
+                         float *first_control /*[2][B]*/, float *losses /*[S][B] or NULL*/,
+                         int32_t *best /*[B] or NULL*/, int64_t B);
 
 int ocd_episode_batch_host(ocd_ctx *ctx, const ocd_params *p, const ocd_scenario *sc,
                            const float *robot_init, const float *other_init,

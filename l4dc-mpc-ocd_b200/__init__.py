@@ -4,13 +4,22 @@
 ``interact_drive``  drop-in mirror of the reference's planner / car / world / MPC_ORD interface
 ``experiments``     the reference's scenario constructors and the run_mpc_ord driver
 """
-from . import _native  # noqa: F401  (raises ImportError when libocd_b200.so has not been built)
-from .engine import (  # noqa: F401
-    Engine, HostContext, PlannerParams, Scenario, MATH_FAST, MATH_PRECISE, OPT_SGD, OPT_LBFGS, device_count, kernel_form,
-)
+import importlib as _importlib
 
 __all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "OPT_SGD", "OPT_LBFGS",
            "device_count", "kernel_form"]
+
+
+def __getattr__(name):
+    """The engine (and with it ``libocd_b200.so``) is loaded on first use, not at package import: helpers that are
+    plain numpy -- ``synthetic``, ``cmaes`` -- stay importable in a process that must not map the CUDA library
+    (bench.py's ``--impl reference`` arm).  Any engine name still raises ImportError when the library has not been
+    built: there is no CPU fallback."""
+    if name in __all__:
+        return getattr(_importlib.import_module(__name__ + ".engine"), name)
+    if name in ("_native", "engine"):
+        return _importlib.import_module(__name__ + "." + name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 def install_as_reference() -> None:

@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libocd_b200.so"
+# OCD_B200_LIB: a variant build of the same library (scripts/tuning/build_variants.sh) for A/B measurements
+LIB_PATH = Path(os.environ["OCD_B200_LIB"]).resolve() if os.environ.get("OCD_B200_LIB") else _HERE / "libocd_b200.so"
 
 ABI_VERSION = 2
 MAX_LANES, MAX_OTHER, MAX_PLAN, MAX_H, MAX_STARTS = 4, 7, 16, 64, 6
@@ -71,6 +74,7 @@ _PROTOTYPES = {
     "ocd_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ocd_ctx_destroy": (None, [_P]),
     "ocd_solve_batch_host": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64]),
+    "ocd_solve_first_host": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64]),
     "ocd_episode_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _P, _I64]),
     "ocd_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
 }

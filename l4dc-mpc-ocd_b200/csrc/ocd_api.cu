@@ -3,6 +3,7 @@
 // operator kernels (reward + gradient, features, dynamics) and the host-buffer layer.
 // Build: make -C l4dc-mpc-ocd_b200/csrc   (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <cmath>
 #include <cstdio>
@@ -47,6 +48,17 @@ OCD_EXTERN_SOLVE(0, 2, 3)
 OCD_EXTERN_SOLVE(0, 3, 3)
 OCD_EXTERN_SOLVE(0, 4, 3)
 OCD_EXTERN_SOLVE(0, 5, 3)
+// the sweep's other two horizons at a compile-time H: 15 (medium: the Q kernels) and 50 (long: constant segment count)
+OCD_EXTERN_SOLVE(15, 1, 3)
+OCD_EXTERN_SOLVE(15, 2, 3)
+OCD_EXTERN_SOLVE(15, 3, 3)
+OCD_EXTERN_SOLVE(15, 4, 3)
+OCD_EXTERN_SOLVE(15, 5, 3)
+OCD_EXTERN_SOLVE(50, 1, 3)
+OCD_EXTERN_SOLVE(50, 2, 3)
+OCD_EXTERN_SOLVE(50, 3, 3)
+OCD_EXTERN_SOLVE(50, 4, 3)
+OCD_EXTERN_SOLVE(50, 5, 3)
 #undef OCD_EXTERN_SOLVE
 
 // ---------------------------------------------------------------------------------------------
@@ -252,15 +264,21 @@ __global__ void __launch_bounds__(kMaxThreads) k_solve_lbfgs(const __grid_consta
         if (!ok) break;
         lbfgs_value_grad(k, gw, wraw, P, x0, y0, v0, th0, oth, P, ut, gt);
         {
+            // the candidate pair goes to scratch (d and q are free here): once the ring is full, slot `head` holds the
+            // oldest pair the two-loop recursion still reads, and a rejected candidate must not overwrite it
             float sy = 0.0f, yy = 0.0f;
             for (int j = 0; j < n; ++j) {
                 const float sj = __fsub_rn(ut[j], u[j]), yj = __fsub_rn(gt[j], g[j]);
-                Sh[head][j] = sj;
-                Yh[head][j] = yj;
+                d[j] = sj;
+                q[j] = yj;
                 sy = __fadd_rn(sy, __fmul_rn(sj, yj));
                 yy = __fadd_rn(yy, __fmul_rn(yj, yj));
             }
             if (yy > 0.0f && sy > __fmul_rn(1e-10f, yy)) {
+                for (int j = 0; j < n; ++j) {
+                    Sh[head][j] = d[j];
+                    Yh[head][j] = q[j];
+                }
                 rho[head] = __fdiv_rn(1.0f, sy);
                 head = (head + 1) % kLbfgsM;
                 if (kk < kLbfgsM) ++kk;
@@ -316,7 +334,9 @@ k_smooth(int kind, const float *z, float a, float b, float c, float *out, long l
     out[i] = r;
 }
 
-// dependent-free FMA loop: 8 independent chains per thread, 2 FLOP per FMA
+// dependent-free FMA loop: 8 independent chains per thread, 512 FFMA per loop trip (so the loop's own counter,
+// compare and branch are 0.6 % of the issue slots; with 64 per trip the probe read 92 % of nominal), 2 FLOP per FMA
+static constexpr int kPeakFmaPerTrip = 512;
 __global__ void __launch_bounds__(256) k_fp32_peak(int iters, float *sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(256) k_fp32_peak(int iters, float *sink) {
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kPeakFmaPerTrip / 8; ++r) {
             a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
             a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
         }
@@ -395,6 +415,14 @@ static int check_weights(const float *weights, long long Bw, const int32_t *idx,
     return OCD_OK;
 }
 
+// host-resident weight_idx (the *_host entry points): every entry must select a column of the table
+static int check_host_idx(const int32_t *idx, long long Bw, long long B) {
+    if (!idx) return OCD_OK;
+    for (long long b = 0; b < B; ++b)
+        if (idx[b] < 0 || idx[b] >= Bw) return OCD_EINVAL;
+    return OCD_OK;
+}
+
 static int pick_P(long long) { return kP; }
 
 // (H, other cars, lanes) specialisations: the shipped scenarios; everything else takes the
@@ -410,15 +438,34 @@ static int pick_P(long long) { return kP; }
         return FN<0, 0, 0, PRECISE>(__VA_ARGS__);                                           \
     } while (0)
 
+// FAST k_solve on three lanes with 1..5 other cars: compile-time car count, and a compile-time horizon for the
+// three horizons of the synthetic sweep (5: register-resident, 15: Q kernels, 50: constant segment count).
+#define OCD_SOLVE_SWITCH(FN, NO_, ...)                                          \
+    do {                                                                        \
+        if (k.H == 15) return FN<15, NO_, 3, false>(__VA_ARGS__);               \
+        if (k.H == 50) return FN<50, NO_, 3, false>(__VA_ARGS__);               \
+        if (NO_ > 1) {                                                          \
+            if (k.H == 5) return FN<5, (NO_ > 1 ? NO_ : 2), 3, false>(__VA_ARGS__); \
+            return FN<0, (NO_ > 1 ? NO_ : 2), 3, false>(__VA_ARGS__);           \
+        }                                                                       \
+    } while (0)
+
+// OCD_RUNTIME_H=1 (tests and tuning, read at every launch): skip the compile-time H = 15 / 50 specialisations, i.e.
+// run those horizons on the runtime-horizon segmented kernels every other horizon uses.
+static bool runtime_h_forced() {
+    const char *e = std::getenv("OCD_RUNTIME_H");
+    return e && e[0] == '1';
+}
+
 static int launch_solve(const KParams &k, bool precise, const SolveArgs &a, cudaStream_t st) {
     if (precise) OCD_DISPATCH(launch_solve_t, true, k, a, st);
-    if (k.L == 3 && k.NO >= 2 && k.NO <= 5) {
-        const bool h5 = k.H == 5;
+    if (k.L == 3 && k.NO >= 1 && k.NO <= 5 && !((k.H == 15 || k.H == 50) && runtime_h_forced())) {
         switch (k.NO) {
-            case 2: return h5 ? launch_solve_t<5, 2, 3, false>(k, a, st) : launch_solve_t<0, 2, 3, false>(k, a, st);
-            case 3: return h5 ? launch_solve_t<5, 3, 3, false>(k, a, st) : launch_solve_t<0, 3, 3, false>(k, a, st);
-            case 4: return h5 ? launch_solve_t<5, 4, 3, false>(k, a, st) : launch_solve_t<0, 4, 3, false>(k, a, st);
-            default: return h5 ? launch_solve_t<5, 5, 3, false>(k, a, st) : launch_solve_t<0, 5, 3, false>(k, a, st);
+            case 1: OCD_SOLVE_SWITCH(launch_solve_t, 1, k, a, st); break;
+            case 2: OCD_SOLVE_SWITCH(launch_solve_t, 2, k, a, st); break;
+            case 3: OCD_SOLVE_SWITCH(launch_solve_t, 3, k, a, st); break;
+            case 4: OCD_SOLVE_SWITCH(launch_solve_t, 4, k, a, st); break;
+            default: OCD_SOLVE_SWITCH(launch_solve_t, 5, k, a, st); break;
         }
     }
     OCD_DISPATCH(launch_solve_t, false, k, a, st);
@@ -433,13 +480,13 @@ static int launch_episode(const KParams &k, bool precise, const ocd_scenario &sc
 // the same two dispatches, asking which kernel form would run (ocd_kernel_form)
 static int form_of(const KParams &k, bool precise, long long B, bool episode) {
     if (precise) OCD_DISPATCH(form_t, true, k, B, episode);
-    if (!episode && k.L == 3 && k.NO >= 2 && k.NO <= 5) {
-        const bool h5 = k.H == 5;
+    if (!episode && k.L == 3 && k.NO >= 1 && k.NO <= 5 && !((k.H == 15 || k.H == 50) && runtime_h_forced())) {
         switch (k.NO) {
-            case 2: return h5 ? form_t<5, 2, 3, false>(k, B, false) : form_t<0, 2, 3, false>(k, B, false);
-            case 3: return h5 ? form_t<5, 3, 3, false>(k, B, false) : form_t<0, 3, 3, false>(k, B, false);
-            case 4: return h5 ? form_t<5, 4, 3, false>(k, B, false) : form_t<0, 4, 3, false>(k, B, false);
-            default: return h5 ? form_t<5, 5, 3, false>(k, B, false) : form_t<0, 5, 3, false>(k, B, false);
+            case 1: OCD_SOLVE_SWITCH(form_t, 1, k, B, false); break;
+            case 2: OCD_SOLVE_SWITCH(form_t, 2, k, B, false); break;
+            case 3: OCD_SOLVE_SWITCH(form_t, 3, k, B, false); break;
+            case 4: OCD_SOLVE_SWITCH(form_t, 4, k, B, false); break;
+            default: OCD_SOLVE_SWITCH(form_t, 5, k, B, false); break;
         }
     }
     OCD_DISPATCH(form_t, false, k, B, episode);
@@ -840,6 +887,23 @@ static void copy_pool_free(CopyPool *p) {
     delete p;
 }
 
+// Staging-copy workers beside the caller: from the cores THIS process may run on (its affinity mask -- with one
+// process per GPU each rank owns a slice of the host, and eight ranks sizing their pools from the whole machine
+// oversubscribed it: 7 workers x 8 ranks on 32 cores), at most 7.  OCD_HOST_THREADS=<n> (copy threads, caller
+// included) overrides it.
+static unsigned copy_workers() {
+    if (const char *e = std::getenv("OCD_HOST_THREADS")) {
+        const long v = std::strtol(e, nullptr, 10);
+        if (v >= 1) return (unsigned)(v - 1 > 15 ? 15 : v - 1);
+    }
+    unsigned cores = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = (unsigned)CPU_COUNT(&set);
+    if (!cores) cores = std::thread::hardware_concurrency();
+    if (cores < 2) return 0;
+    return cores - 1 > 7 ? 7 : cores - 1;
+}
+
 static void copy_rows(CopyPool *pool, char *dst, size_t dst_stride, const char *src, size_t src_stride, int rows,
                       size_t bytes) {
     const size_t total = (size_t)rows * bytes;
@@ -848,8 +912,7 @@ static void copy_rows(CopyPool *pool, char *dst, size_t dst_stride, const char *
         local.span(0, total);
         return;
     }
-    const unsigned hw = std::thread::hardware_concurrency();
-    const unsigned nw = hw >= 16 ? 7 : (hw >= 4 ? hw / 2 - 1 : 0);          // workers beside the caller
+    const unsigned nw = copy_workers();                                       // workers beside the caller
     std::shared_ptr<CopyJob> j;
     try {                                                                     // nothing may throw across the C ABI
         if (nw && pool->start(nw)) j = std::make_shared<CopyJob>();
@@ -876,10 +939,13 @@ static void copy_rows(CopyPool *pool, char *dst, size_t dst_stride, const char *
 // strided 2-D copy); pageable memory goes through the context's pinned staging area.
 struct HostArray {
     char  *user;        // host array [rows][B] of `elem`-byte items (null: absent)
-    int    rows;
+    int    rows;        // rows of the device buffer
     size_t elem;
     bool   pinned;
     size_t dev_off, pin_off;    // per-chunk compact [rows][n] buffers in the device / pinned arena
+    int    rows_out = -1;       // outputs: rows copied back to `user` ([rows_out][B]; -1: all of them)
+    bool   dev_only = false;    // output the caller did not ask for: the kernel writes it, nothing comes back
+    int    out_rows() const { return rows_out < 0 ? rows : rows_out; }
 };
 
 static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, cudaStream_t st) {
@@ -898,21 +964,22 @@ static int h2d_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int6
 }
 
 static int d2h_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n, cudaStream_t st) {
-    const char *src = c->dev + a.dev_off + (size_t)a.rows * b0 * a.elem;
+    if (a.dev_only) return OCD_OK;
+    const char *src = c->dev + a.dev_off + (size_t)a.rows * b0 * a.elem;     // the first out_rows() rows of the chunk
     cudaError_t e;
     if (a.pinned)
-        e = cudaMemcpy2DAsync(a.user + b0 * a.elem, B * a.elem, src, n * a.elem, n * a.elem, a.rows,
+        e = cudaMemcpy2DAsync(a.user + b0 * a.elem, B * a.elem, src, n * a.elem, n * a.elem, a.out_rows(),
                               cudaMemcpyDeviceToHost, st);
     else
         e = cudaMemcpyAsync(c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem, src,
-                            (size_t)a.rows * n * a.elem, cudaMemcpyDeviceToHost, st);
+                            (size_t)a.out_rows() * n * a.elem, cudaMemcpyDeviceToHost, st);
     return e == cudaSuccess ? OCD_OK : OCD_ECUDA;
 }
 
 static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0, int64_t n) {
-    if (a.pinned) return;
+    if (a.pinned || a.dev_only) return;
     const char *stage = c->pin + a.pin_off + (size_t)a.rows * b0 * a.elem;
-    copy_rows(c->pool, a.user + b0 * a.elem, B * a.elem, stage, n * a.elem, a.rows, n * a.elem);
+    copy_rows(c->pool, a.user + b0 * a.elem, B * a.elem, stage, n * a.elem, a.out_rows(), n * a.elem);
 }
 
 // The batch is cut into column chunks that flow through four streams linked by per-chunk events: one
@@ -920,15 +987,19 @@ static void unstage_chunk(ocd_ctx *c, const HostArray &a, int64_t B, int64_t b0,
 // buffers), two compute lanes take the chunks alternately (so that one kernel's tail wave is filled by the
 // next kernel's blocks), one stream drains results through the D2H copy engine.  The SMs never wait for
 // a copy after the first chunk and the call costs about max(copy, solve) instead of their sum.
-int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
-                         int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
-                         const float *cur_speed, float *plan, float *losses, int32_t *best, int64_t B) {
+// plan_rows: rows of the plan [H][2][B] that travel back (2 H: the whole plan; 2: the first control only);
+// losses / best may be null when plan_rows == 2 (the kernel still writes them on the device, nothing comes back).
+static int solve_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
+                      int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
+                      const float *cur_speed, float *plan, int plan_rows, float *losses, int32_t *best, int64_t B) {
     KParams k;
     int rc = digest(p, k);
     if (rc) return rc;
     if (B == 0) return OCD_OK;
-    if (!c || !world || !plan || !losses || !best || B < 0) return OCD_EINVAL;
+    if (!c || !world || !plan || B < 0) return OCD_EINVAL;
+    if (plan_rows != 2 && (!losses || !best)) return OCD_EINVAL;
     if ((rc = check_weights(weights, Bw, weight_idx, B))) return rc;
+    if ((rc = check_host_idx(weight_idx, Bw, B))) return rc;
     if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
     if (cudaSetDevice(c->device) != cudaSuccess) return OCD_ECUDA;
     const int C = k.NO + 1;
@@ -943,15 +1014,15 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     HostArray a_w{per_problem_w ? (char *)weights : nullptr, k.K, 4, is_pinned(weights), 0, 0};
     HostArray a_oc{per_problem_oc ? (char *)other_controls : nullptr, k.NO * k.H * 2, 4, is_pinned(other_controls), 0, 0};
     HostArray a_cs{(char *)cur_speed, 1, 4, is_pinned(cur_speed), 0, 0};
-    HostArray a_plan{(char *)plan, k.H * 2, 4, is_pinned(plan), 0, 0};
-    HostArray a_loss{(char *)losses, k.S, 4, is_pinned(losses), 0, 0};
-    HostArray a_best{(char *)best, 1, 4, is_pinned(best), 0, 0};
+    HostArray a_plan{(char *)plan, k.H * 2, 4, is_pinned(plan), 0, 0, plan_rows};
+    HostArray a_loss{(char *)losses, k.S, 4, is_pinned(losses), 0, 0, -1, losses == nullptr};
+    HostArray a_best{(char *)best, 1, 4, is_pinned(best), 0, 0, -1, best == nullptr};
     HostArray *arrays[] = {&a_world, &a_idx, &a_w, &a_oc, &a_cs, &a_plan, &a_loss, &a_best};
     Arena dev, pin;
     for (HostArray *a : arrays)
-        if (a->user) {
+        if (a->user || a->dev_only) {
             a->dev_off = dev.take((size_t)a->rows * B * a->elem);
-            if (!a->pinned) a->pin_off = pin.take((size_t)a->rows * B * a->elem);
+            if (!a->pinned && !a->dev_only) a->pin_off = pin.take((size_t)a->rows * B * a->elem);
         }
     // shared (not per-problem) inputs: copied once, in full -- straight from the user's array when it is
     // page-locked, through the staging area otherwise
@@ -972,7 +1043,7 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
         return OCD_ECUDA;
 
     auto chunk_ptr = [&](const HostArray &a, int ch) -> char * {
-        return a.user ? c->dev + a.dev_off + (size_t)a.rows * start[ch] * a.elem : nullptr;
+        return (a.user || a.dev_only) ? c->dev + a.dev_off + (size_t)a.rows * start[ch] * a.elem : nullptr;
     };
     cudaStream_t s_in = c->lanes[0], s_out = c->lanes[3];
     for (int ch = 0; ch < nchunks && rc == OCD_OK; ++ch) {
@@ -1009,6 +1080,21 @@ int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, co
     return OCD_OK;
 }
 
+int ocd_solve_batch_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
+                         int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
+                         const float *cur_speed, float *plan, float *losses, int32_t *best, int64_t B) {
+    if (!losses || !best) return OCD_EINVAL;
+    return solve_host(c, p, world, other_controls, Bo, weights, Bw, weight_idx, cur_speed, plan, p ? 2 * p->H : 0, losses,
+                      best, B);
+}
+
+int ocd_solve_first_host(ocd_ctx *c, const ocd_params *p, const float *world, const float *other_controls,
+                         int64_t Bo, const float *weights, int64_t Bw, const int32_t *weight_idx,
+                         const float *cur_speed, float *first_control, float *losses, int32_t *best, int64_t B) {
+    return solve_host(c, p, world, other_controls, Bo, weights, Bw, weight_idx, cur_speed, first_control, 2, losses,
+                      best, B);
+}
+
 int ocd_episode_batch_host(ocd_ctx *c, const ocd_params *p, const ocd_scenario *sc, const float *robot_init,
                            const float *other_init, const float *plan_weights, int64_t Bw,
                            const int32_t *weight_idx, const float *true_weights, const int32_t *unlucky_idx,
@@ -1018,6 +1104,7 @@ int ocd_episode_batch_host(ocd_ctx *c, const ocd_params *p, const ocd_scenario *
     if (rc) return rc;
     if (!c || !sc || !robot_init || !true_weights || !returns || B < 0) return OCD_EINVAL;
     if ((rc = check_weights(plan_weights, Bw, weight_idx, B))) return rc;
+    if ((rc = check_host_idx(weight_idx, Bw, B))) return rc;
     if (B == 0) return OCD_OK;
     if (cudaSetDevice(c->device) != cudaSuccess) return OCD_ECUDA;
     Arena ar;
@@ -1060,17 +1147,18 @@ int ocd_fp32_peak(int iters, double *flops, void *stream) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = sms * 8, threads = 256;
-    k_fp32_peak<<<blocks, threads, 0, st>>>(iters / 4 + 1, sink);   // warm-up
+    const int blocks = sms * 16, threads = 256;
+    const int trips = (iters + 7) / 8;                              // `iters` keeps its meaning: rounds of 64 FMAs
+    k_fp32_peak<<<blocks, threads, 0, st>>>(trips / 4 + 1, sink);   // warm-up
     double best = 0.0;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0, st);
-        k_fp32_peak<<<blocks, threads, 0, st>>>(iters, sink);
+        k_fp32_peak<<<blocks, threads, 0, st>>>(trips, sink);
         cudaEventRecord(e1, st);
         if (cudaEventSynchronize(e1) != cudaSuccess) break;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads / (ms * 1e-3);
+        const double fl = 2.0 * kPeakFmaPerTrip * (double)trips * (double)blocks * threads / (ms * 1e-3);
         if (fl > best) best = fl;
     }
     cudaEventDestroy(e0);

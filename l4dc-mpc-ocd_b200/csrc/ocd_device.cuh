@@ -779,6 +779,128 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Medium compile-time horizons (HT = 9..24, FAST): the register file holds the controls and the saved
+// (v, cos, sin) of every step, but not the four other values the reverse sweep needs per step -- the step
+// length d_t and the feature gradient (gx, hy, ke).  Those four travel through shared memory as ONE float4 per
+// step: one STS.128 in the forward sweep, one LDS.128 in the reverse sweep (row of HT float4 per thread, rows an
+// odd number of float4 apart: conflict-free quarter-warps, base + immediate addressing).  Nothing is recomputed
+// -- the segmented kernels pay a second dynamics pass with its two MUFU per step -- and the arithmetic is the
+// register-resident kernels' own, statement for statement.
+// ---------------------------------------------------------------------------------------------
+#ifndef OCD_Q_SF
+#define OCD_Q_SF 0
+#endif
+__host__ __device__ inline int q_stride(int H) { return H | 1; }     // float4 per thread row
+
+// OCD_Q_CS = 1 (tuning): the saved (cos, sin) of every step travel through shared memory too (one float2 per step,
+// rows of HT + 1 float2 behind the float4 rows), which leaves only v_t and the controls in registers.
+#ifndef OCD_Q_CS
+#define OCD_Q_CS 0
+#endif
+__host__ __device__ inline int q2_stride(int H) { return (H + 1) | 1; }                 // float2 per thread row
+__host__ __device__ inline int q_thread_floats(int H) { return 4 * q_stride(H) + (OCD_Q_CS ? 2 * q2_stride(H) : 0); }
+
+template <int HT, int NOT_, int LT, int VM, bool SF>
+__device__ __forceinline__ void forward_sweep_q(const KParams &k, const GradW &w, float x0, float y0, float v0,
+                                                float th0, float sn0, float cs0, const float *oth, int P,
+                                                const Traj<HT> &u, float *sv, float *sc, float *ss, float4 *q,
+                                                float2 *q2, bool &flag) {
+    constexpr int NO = NOT_;
+    float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
+#pragma unroll
+    for (int t = 0; t < HT; ++t) {
+        if (SF) {
+            int one;
+            asm volatile("mov.u32 %0, 1;" : "=r"(one));
+            if (one == 0) continue;
+        }
+        const float ac = fmaxf(fminf(u.ua[t], 4.0f), -8.0f);
+        const float oc = fmaxf(fminf(u.uw[t], 4.0f), -4.0f);
+        const float total = fmaf(-k.mu, v * v, ac);
+        const float dist = fmaf(total, k.hdt2, v * k.dt);
+        sv[t] = v;
+        if (OCD_Q_CS) {
+            if (t > 0) q2[t] = make_float2(cs, sn);           // (cos, sin) of th_0 stay in registers
+        } else {
+            sc[t] = cs; ss[t] = sn;
+        }
+        x = fmaf(cs, dist, x);
+        y = fmaf(sn, dist, y);
+        v = fmaf(total, k.dt, v);
+        th = fmaf(oc, k.dt, th);
+        Mth<false>::sincos_(th, sn, cs);
+        float gx, hy, ke, unused;
+        feature_grad<NOT_, LT, false, false, VM>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P, gx, hy, ke,
+                                                 unused, 0.0f, flag);
+        q[t] = make_float4(dist, gx, hy, ke);
+    }
+    sv[HT] = v; sc[HT] = cs; ss[HT] = sn;
+}
+
+template <int HT, int NOT_, int LT, int LAT>
+__device__ __forceinline__ void sgd_iteration_q(const KParams &k, const GradW &w, float x0, float y0, float v0,
+                                                float th0, float sn0, float cs0, const float *oth, int P,
+                                                Traj<HT> &u, float4 *q, float2 *q2) {
+    float sv[HT + 1], sc[HT + 1], ss[HT + 1];
+    bool flag = false;
+    if (LAT != 0) {
+        forward_sweep_q<HT, NOT_, LT, 1, (OCD_Q_SF != 0 || (LAT == 2 && NOT_ >= 3))>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P,
+                                                                                    u, sv, sc, ss, q, q2, flag);
+        if (__any_sync(OCD_FULL, flag))
+            forward_sweep_q<HT, NOT_, LT, 0, false>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
+    } else {
+        forward_sweep_q<HT, NOT_, LT, 0, false>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
+    }
+    float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
+    const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
+    const float lra = k.lr * k.hdt2, lrv = k.lr * k.dt;
+    float cn = sc[HT], snn = ss[HT];                       // (cos, sin) of th_{t+1}
+#pragma unroll
+    for (int tt = 0; tt < HT; ++tt) {
+        const int t = HT - 1 - tt;
+        const float4 g = q[t];                               // (d_t, gx, hy, ke) at s_{t+1}
+        float ct, st;                                        // (cos, sin) of th_t
+        if (OCD_Q_CS) {
+            if (t > 0) {
+                const float2 c = q2[t];
+                ct = c.x; st = c.y;
+            } else {
+                ct = cs0; st = sn0;
+            }
+        } else {
+            ct = sc[t]; st = ss[t];
+        }
+        const float mx = g.y + lx;
+        const float my = fmaf(w.wcy, g.z, ly);
+        const float mv = fmaf(g.w, snn, lv);
+        const float mth = fmaf(__fmul_rn(g.w, sv[t + 1]), cn, lth);
+        const float ld = fmaf(ct, mx, st * my);
+        const float a = u.ua[t], om = u.uw[t];
+        const bool in_a = (a >= -8.0f) && (a <= 4.0f);
+        const bool in_w = fabsf(om) <= 4.0f;
+        lv = fmaf(fmaf(c1, sv[t], 1.0f), mv, fmaf(c2, sv[t], k.dt) * ld);
+        lth = fmaf(g.x, fmaf(ct, my, -(st * mx)), mth);
+        lx = mx;
+        ly = my;
+        cn = ct; snn = st;
+        u.ua[t] = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
+        u.uw[t] = in_w ? fmaf(lrv, mth, om) : om;
+    }
+}
+
+template <int HT, int NOT_, int LT, int LAT>
+__device__ __forceinline__ float solve_start_q(const KParams &k, const GradW &w, const float *wraw, int ws, float x0,
+                                               float y0, float v0, float th0, const float *oth, int P, Traj<HT> &u,
+                                               float4 *q, float2 *q2) {
+    float sn0, cs0;
+    Mth<false>::sincos_(th0, sn0, cs0);
+#pragma unroll 1
+    for (int it = 0; it < k.n_iter; ++it)
+        sgd_iteration_q<HT, NOT_, LT, LAT>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, q, q2);
+    return -rollout_reward<HT, LT, false, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Time-parallel solve: the lowest-latency path, for batches so small that even the latency variant
 // leaves the GPU idle (the reference's real configurations: 45-180 episodes).  kTG = 8 consecutive
 // lanes share one (problem, start); lane t owns horizon step t (HT <= kTG; spare lanes shadow the
@@ -888,7 +1010,7 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 // [H][2] and checkpoints [nseg][4] live in shared memory, thread index fastest.
 // ---------------------------------------------------------------------------------------------
 // Forward half of pass 2 of one segment: from the segment's start state, with the feature gradients.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int VM, bool SF = false>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int VM, bool SF = false, bool FR = false>
 __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, float x, float y, float v, float th,
                                             const float *os, int ostep, int P, const float *us, int rem, float tbase,
                                             float *ua, float *uw, float *sv, float *sc, float *ss, float *sd, float *gx,
@@ -917,7 +1039,7 @@ __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, fl
             v = fmaf(total, k.dt, v);
             th = fmaf(oc, k.dt, th);
             Mth<PRECISE>::sincos_(th, sn, cs);
-            feature_grad<NOT_, LT, PRECISE, LIN, VM, !PRECISE, false>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
+            feature_grad<NOT_, LT, PRECISE, LIN, VM, !PRECISE, FR>(k, w, x, y, v, sn, cs, ot, LIN ? 4 * P : 2 * P, P,
                                                                    gx[i], gy[i], gv[i], gth[i], tbase + (float)(i + 1),
                                                                    flag);
             sv[i + 1] = v; sc[i + 1] = cs; ss[i + 1] = sn;      // the state after step i (overwritten by step i+1's own save)
@@ -930,7 +1052,7 @@ __device__ __forceinline__ void seg_forward(const KParams &k, const GradW &w, fl
 // runs straight-line (vote mode 1) and is repeated with the exact rules if a lane asked for one.
 // Step fences in the segmented wide form: measured, they help with two or more other cars (H=15, 6 cars: 8.40 ->
 // 7.65 ms) and cost with one (4.74 -> 4.84 ms), so they follow the car count.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int LAT>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, bool FULL, int LAT, bool FR = false>
 __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, float x, float y, float v, float th,
                                           const float *os, int ostep, int P, float *us, int rem, float tbase,
                                           float (&lam)[4]) {
@@ -938,14 +1060,14 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
     bool flag = false;
     if (LAT != 0 && !PRECISE) {
         constexpr bool SF = LAT == 2 && NOT_ != 1;
-        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 1, SF>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv,
-                                                              sc, ss, sd, gx, gy, gv, gth, flag);
+        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 1, SF, FR>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw,
+                                                                  sv, sc, ss, sd, gx, gy, gv, gth, flag);
         if (__any_sync(OCD_FULL, flag))
-            seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv,
-                                                              sc, ss, sd, gx, gy, gv, gth, flag);
+            seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0, false, FR>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua,
+                                                                         uw, sv, sc, ss, sd, gx, gy, gv, gth, flag);
     } else {
-        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw, sv, sc,
-                                                          ss, sd, gx, gy, gv, gth, flag);
+        seg_forward<SEG, NOT_, LT, PRECISE, LIN, FULL, 0, false, FR>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, ua, uw,
+                                                                     sv, sc, ss, sd, gx, gy, gv, gth, flag);
     }
     float lx = lam[0], ly = lam[1], lv = lam[2], lth = lam[3];
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
@@ -980,10 +1102,12 @@ __device__ __forceinline__ void seg_pass2(const KParams &k, const GradW &w, floa
     lam[0] = lx; lam[1] = ly; lam[2] = lv; lam[3] = lth;
 }
 
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0>
+// HC > 0: the horizon is a compile-time constant (segment count and the length of the last segment fold away).
+// FR: the register-resident kernels' folded lane term and single-reciprocal bump / fence (feature_grad's FOLD).
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0, int HC = 0, bool FR = false>
 __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                   float th0, const float *oth, int P, const SmemTraj &u, float *ck) {
-    const int H = k.H;
+    const int H = HC > 0 ? HC : k.H;
     const int NO = NOT_ > 0 ? NOT_ : k.NO;
     const int nseg = (H + SEG - 1) / SEG;
     {   // pass 1: dynamics only; the state at the start of segments 1.. is checkpointed (segment 0 starts at
@@ -1024,7 +1148,7 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             const float4 st = *reinterpret_cast<const float4 *>(c);
             x = st.x; y = st.y; v = st.z; th = st.w;
         }
-        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false, LAT>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, false, LAT, FR>(k, w, x, y, v, th, os, ostep, P, us, rem, tbase, lam);
         --sg; us -= 2 * SEG; c -= 4; os -= SEG * ostep; tbase -= (float)SEG;
     }
 #pragma unroll 1
@@ -1034,12 +1158,12 @@ __device__ __forceinline__ void sgd_iteration_seg(const KParams &k, const GradW 
             const float4 st = *reinterpret_cast<const float4 *>(c);
             x = st.x; y = st.y; v = st.z; th = st.w;
         }
-        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true, LAT>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
+        seg_pass2<SEG, NOT_, LT, PRECISE, LIN, true, LAT, FR>(k, w, x, y, v, th, os, ostep, P, us, SEG, tbase, lam);
     }
 }
 
 // The complete segmented solve for one (problem, start): start controls, n_iter iterations, final loss.
-template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0>
+template <int SEG, int NOT_, int LT, bool PRECISE, bool LIN, int LAT = 0, int HC = 0, bool FR = false>
 __device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &w, const float *wraw, int ws,
                                                  float x0, float y0, float v0, float th0, const float *oth, int P,
                                                  int s, float cur_speed, const SmemTraj &u, float *ck) {
@@ -1051,7 +1175,7 @@ __device__ __forceinline__ float solve_start_seg(const KParams &k, const GradW &
     }
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
-        sgd_iteration_seg<SEG, NOT_, LT, PRECISE, LIN, LAT>(k, w, x0, y0, v0, th0, oth, P, u, ck);
+        sgd_iteration_seg<SEG, NOT_, LT, PRECISE, LIN, LAT, HC, FR>(k, w, x0, y0, v0, th0, oth, P, u, ck);
     return -rollout_reward<0, LT, PRECISE, SmemTraj, LIN>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 

@@ -35,9 +35,24 @@ namespace ocd {
 // with one other car, and with three at a compile-time horizon (which would otherwise settle just above 128), and
 // to 168 (three warps) elsewhere: measured against 112 / 128 / 168 on every shape of the sweep
 // (scripts/tuning/wide_regs.sh); it is the fastest form for large batches of most shapes (see pick_form).
+// The medium-horizon kernels (HT = 9..24, "Q" kernels: controls and saved states in registers, the rest of the
+// reverse sweep's inputs through shared memory) run straight-line code in every form: OCD_Q_REGS registers
+// (wide and throughput form), 255 for the latency form.
+#ifndef OCD_Q_REGS
+#define OCD_Q_REGS 128
+#endif
+#define OCD_IS_Q(HT) ((HT) >= 9 && (HT) <= 24)
+// Long compile-time horizons (HT >= 25, FAST): the segmented adjoint with a constant segment count
+#define OCD_IS_SEGC(HT) ((HT) >= 25)
+#ifndef OCD_SEGC_REGS
+#define OCD_SEGC_REGS 168
+#endif
+#ifndef OCD_SEGC_FR
+#define OCD_SEGC_FR 1
+#endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96)))
+    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT) ? OCD_Q_REGS : OCD_IS_SEGC(HT) ? OCD_SEGC_REGS : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -78,8 +93,15 @@ struct EpisodeArgs {
     int          P;
 };
 
+// Column of the weight table problem b plans with.  An index outside [0, Bw) is clamped: the *_host entry points
+// and the Python front-end reject such batches before the launch (OCD_EINVAL / ValueError); for device-resident
+// indices, which the launcher cannot inspect without a synchronising copy, clamping keeps a bad index from
+// becoming an out-of-bounds read.
 __device__ __forceinline__ long long weight_column(const int32_t *idx, long long Bw, long long b) {
-    if (idx) return (long long)idx[b];
+    if (idx) {
+        const long long i = (long long)idx[b];
+        return i < 0 ? 0 : (i >= Bw ? Bw - 1 : i);
+    }
     return Bw == 1 ? 0 : b;
 }
 
@@ -93,6 +115,7 @@ struct Smem {
     float *wtrue;   // [K]             true weights (episode only)
     float *useg;    // [S*P][2H | 1]     controls of every thread (segmented kernels only)
     float *ckpt;    // [S*P][4 nseg | 1] segment-start states (segmented kernels only)
+    float4 *q;      // [S*P][H | 1]      (d_t, gx, hy, ke) of every step (medium-horizon Q kernels only; first in the carve-up)
 };
 
 static constexpr int kSeg = 5;    // steps per segment of the runtime-horizon kernels (register budget of the H=5 kernel)
@@ -103,15 +126,20 @@ __host__ __device__ inline bool slab_is_linear(bool seg, bool precise, int other
     return seg && !precise && other_mode == 0 && (H * NO >= 100 || H >= 32);
 }
 
-__host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode, bool seg, bool lin) {
+__host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P, bool episode, bool seg, bool lin,
+                                              bool qk = false) {
     size_t n = (size_t)(lin ? 4 * NO : H * NO * 2) * P + (size_t)K * P + (size_t)S * P;
     if (episode) n += (size_t)S * 2 * P + (size_t)(NO + 1) * 4 * P + ((K + 3) / 4) * 4;
     if (seg) n += (size_t)S * P * (seg_u_stride(H) + seg_ck_stride(H, kSeg));
+    if (qk) n += (size_t)S * P * q_thread_floats(H);
     return n;
 }
 
-__device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool episode, bool seg, bool lin) {
+__device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool episode, bool seg, bool lin,
+                                      bool qk = false) {
     Smem m;
+    m.q = reinterpret_cast<float4 *>(base);            // 16-byte aligned: the float4 rows come first
+    if (qk) base += (size_t)k.S * P * q_thread_floats(k.H);
     m.oth = base;
     m.wraw = m.oth + (size_t)(lin ? 4 * k.NO : k.H * k.NO * 2) * P;
     m.loss = m.wraw + (size_t)k.K * P;
@@ -168,9 +196,10 @@ __global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
-    constexpr bool SEGK = (HT == 0);     // runtime horizon: segmented adjoint, controls in shared memory
+    constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT);   // runtime or long horizon: segmented adjoint, controls in shared memory
+    constexpr bool QK = OCD_IS_Q(HT) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
     const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
-    const Smem m = carve(smem_raw, k, P, false, SEGK, lin);
+    const Smem m = carve(smem_raw, k, P, false, SEGK, lin, QK);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
     const bool live = b_raw < a.B;
@@ -197,26 +226,32 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     const float speed = a.cur_speed ? a.cur_speed[b] : v0;
     const int H = HT > 0 ? HT : k.H;
-    Traj<(HT > 0 ? HT : 1)> u;                       // register-resident controls (compile-time horizon)
+    Traj<(SEGK ? 1 : HT)> u;                         // register-resident controls (short and medium compile-time horizons)
     const SmemTraj us{SEGK ? m.useg + (size_t)threadIdx.x * seg_u_stride(k.H) : nullptr};   // shared-memory controls
     float loss;
-    if (SEGK) {
+    if constexpr (SEGK) {
+        constexpr int HC = HT;                       // 0: runtime horizon
+        constexpr bool FR = HC > 0 && OCD_SEGC_FR && !PRECISE;
         float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
         loss = (!PRECISE && lin)
-                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
-                                                                              m.oth + p, P, s, speed, us, ck)
-                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
-                                                                          m.oth + p, P, s, speed, us, ck);
+                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                                      m.oth + p, P, s, speed, us, ck)
+                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                                                                                  m.oth + p, P, s, speed, us, ck);
+    } else if constexpr (QK) {
+        init_start<HT>(k, s, speed, u);
+        loss = solve_start_q<HT, NOT_, LT, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u,
+                                                m.q + (size_t)threadIdx.x * q_stride(HT),
+                                                reinterpret_cast<float2 *>(m.q + (size_t)k.S * P * q_stride(HT)) + (size_t)threadIdx.x * q2_stride(HT));
     } else {
-        init_start<(HT > 0 ? HT : 1)>(k, s, speed, u);
-        loss = solve_start<(HT > 0 ? HT : 1), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P,
-                                                                      u);
+        init_start<(SEGK ? 1 : HT)>(k, s, speed, u);
+        loss = solve_start<(SEGK ? 1 : HT), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
     }
     m.loss[s * P + p] = loss;
     if (live) {
         a.losses[(size_t)s * B + b] = loss;
         if (a.all_plans) {
-#pragma unroll(HT > 0 ? HT : 1)
+#pragma unroll(SEGK ? 1 : HT)
             for (int t = 0; t < H; ++t) {
                 a.all_plans[((size_t)(s * H + t) * 2 + 0) * B + b] = SEGK ? us.acc(t) : u.acc(SEGK ? 0 : t);
                 a.all_plans[((size_t)(s * H + t) * 2 + 1) * B + b] = SEGK ? us.ang(t) : u.ang(SEGK ? 0 : t);
@@ -233,7 +268,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     }
     if (live && s == bi) {
         a.best[b] = bi;
-#pragma unroll(HT > 0 ? HT : 1)
+#pragma unroll(SEGK ? 1 : HT)
         for (int t = 0; t < H; ++t) {
             a.plan[(size_t)(t * 2 + 0) * B + b] = SEGK ? us.acc(t) : u.acc(SEGK ? 0 : t);
             a.plan[(size_t)(t * 2 + 1) * B + b] = SEGK ? us.ang(t) : u.ang(SEGK ? 0 : t);
@@ -626,15 +661,18 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 inline int choose_form(const KParams &k, long long B, bool episode) {
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;          // compile-time horizon and car count
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;                       // segmented kernels (solve only)
+    constexpr bool REGRES = HT > 0 && !OCD_IS_Q(HT) && !OCD_IS_SEGC(HT);  // register-resident (short) horizons
     if (HAS_LAT && HT <= kTG && tiny_batch(B, k.S)) return 3;
     if (episode) return pick_form(B, kP, k.S, HAS_LAT, HAS_LAT && NOT_ == 1, NOT_ == 1, true);
-    return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, HT > 0 && NOT_ == 1, false, HT > 0 && NOT_ >= 3);
+    return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, REGRES && NOT_ == 1, false, REGRES && NOT_ >= 3);
 }
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
-    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, HT == 0,
-                                     slab_is_linear(HT == 0, PRECISE, k.other_mode, k.H, k.NO)) * sizeof(float);
+    constexpr bool SEGK = HT == 0 || OCD_IS_SEGC(HT);
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, SEGK,
+                                     slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO),
+                                     OCD_IS_Q(HT) && !PRECISE) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     constexpr bool ANY_LAT = HAS_LAT || (HT == 0 && !PRECISE);
     const int form = choose_form<HT, NOT_, LT, PRECISE>(k, a.B, false);

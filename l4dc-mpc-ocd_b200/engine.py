@@ -110,6 +110,17 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _check_soa(name: str, t: Optional[torch.Tensor], dtype, device, shape) -> None:
+    """The *_soa entry points hand raw device pointers to the kernels: a tensor of another dtype, device, layout or
+    shape would be reinterpreted, so it is refused here (ValueError, like the reference's shape checks)."""
+    if t is None:
+        return
+    if not torch.is_tensor(t) or t.dtype != dtype or t.device != device or not t.is_contiguous() \
+            or tuple(t.shape) != tuple(shape):
+        got = (tuple(t.shape), t.dtype, t.device, t.is_contiguous()) if torch.is_tensor(t) else type(t)
+        raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {device}, got {got}")
+
+
 FORM_NAMES = {N.FORM_THROUGHPUT: "throughput", N.FORM_LATENCY: "latency", N.FORM_WIDE: "wide",
               N.FORM_TIME_PARALLEL: "time-parallel"}
 
@@ -171,6 +182,12 @@ class Engine:
         Bw = w.shape[0]
         idx = None
         if weight_idx is not None:
+            if not torch.is_tensor(weight_idx) or not weight_idx.is_cuda:
+                # host-side indices are checked before the upload (device-resident ones are clamped by the kernels:
+                # checking them here would cost a synchronising copy)
+                wi = np.asarray(weight_idx.cpu() if torch.is_tensor(weight_idx) else weight_idx)
+                if wi.size and (wi.min() < 0 or wi.max() >= Bw):
+                    raise ValueError(f"weight_idx must lie in [0, {Bw}), got [{wi.min()}, {wi.max()}]")
             idx = self._i32(weight_idx, (B,))
         elif Bw not in (1, B):
             raise ValueError(f"{Bw} weight vectors for {B} problems need a weight_idx")
@@ -183,6 +200,20 @@ class Engine:
         losses [S][B], best [B] (+ all_plans [S][H][2][B])."""
         B = world.shape[-1]
         dev = self.device
+        f32, i32 = torch.float32, torch.int32
+        _check_soa("world", world, f32, dev, (p.C, 4, B))
+        _check_soa("weights", weights, f32, dev, (p.K, Bw))
+        _check_soa("weight_idx", weight_idx, i32, dev, (B,))
+        _check_soa("cur_speed", cur_speed, f32, dev, (B,))
+        if p.other_mode == 1:
+            if other_controls is None or Bo not in (1, B):
+                raise ValueError("other_mode=1 needs other_controls [C-1][H][2][Bo] with Bo in (1, B)")
+            _check_soa("other_controls", other_controls, f32, dev, (p.C - 1, p.H, 2, Bo))
+        if out is not None:
+            _check_soa("out['plan']", out["plan"], f32, dev, (p.H, 2, B))
+            _check_soa("out['losses']", out["losses"], f32, dev, (p.S, B))
+            _check_soa("out['best']", out["best"], i32, dev, (B,))
+            _check_soa("out['all_plans']", out.get("all_plans"), f32, dev, (p.S, p.H, 2, B))
         if out is None:
             out = dict(plan=torch.empty((p.H, 2, B), dtype=torch.float32, device=dev),
                        losses=torch.empty((p.S, B), dtype=torch.float32, device=dev),
@@ -205,6 +236,19 @@ class Engine:
         (+ controls [T][2][B], best [T][B], states [T][C][4][B], final_world [C][4][B])."""
         B = robot_init.shape[-1]
         dev = self.device
+        f32, i32 = torch.float32, torch.int32
+        _check_soa("robot_init", robot_init, f32, dev, (4, B))
+        _check_soa("plan_weights", plan_weights, f32, dev, (p.K, Bw))
+        _check_soa("true_weights", true_weights, f32, dev, (p.K,))
+        _check_soa("weight_idx", weight_idx, i32, dev, (B,))
+        _check_soa("other_init", other_init, f32, dev, (p.C - 1, 4, B))
+        _check_soa("unlucky_idx", unlucky_idx, i32, dev, (B,))
+        if out is not None:
+            _check_soa("out['returns']", out["returns"], f32, dev, (B,))
+            _check_soa("out['controls']", out.get("controls"), f32, dev, (T, 2, B))
+            _check_soa("out['best']", out.get("best"), i32, dev, (T, B))
+            _check_soa("out['states']", out.get("states"), f32, dev, (T, p.C, 4, B))
+            _check_soa("out['final_world']", out.get("final_world"), f32, dev, (p.C, 4, B))
         if out is None:
             out = dict(returns=torch.empty((B,), dtype=torch.float32, device=dev))
             if trace:
@@ -445,6 +489,36 @@ class HostContext:
                                         vp(cs), vp(plan), vp(losses), vp(best), B)
         N.check(rc, "ocd_solve_batch_host")
         return dict(plan=plan, losses=losses, best=best)
+
+    def solve_first_soa(self, p: PlannerParams, world: np.ndarray, weights: np.ndarray, weight_idx=None,
+                        other_controls=None, cur_speed=None, out=None, losses: bool = True, best: bool = True):
+        """The receding-horizon caller's solve (`ocd_solve_first_host`): only plan[0] comes back.
+        Host SoA arrays in; -> dict(first [2][B] (+ losses [S][B], best [B])).  `out` may hold preallocated arrays."""
+        world = np.ascontiguousarray(world, np.float32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        B, Bw = world.shape[-1], weights.shape[-1]
+        idx = None if weight_idx is None else np.ascontiguousarray(weight_idx, np.int32)
+        oc = None if other_controls is None else np.ascontiguousarray(other_controls, np.float32)
+        Bo = 0 if oc is None else oc.shape[-1]
+        cs = None if cur_speed is None else np.ascontiguousarray(cur_speed, np.float32)
+        if out is None:
+            out = dict(first=np.empty((2, B), np.float32))
+            if losses:
+                out["losses"] = np.empty((p.S, B), np.float32)
+            if best:
+                out["best"] = np.empty((B,), np.int32)
+        first, lo, be = out["first"], out.get("losses"), out.get("best")
+        ok = first.shape == (2, B) and first.dtype == np.float32 and first.flags.c_contiguous
+        ok = ok and (lo is None or (lo.shape == (p.S, B) and lo.dtype == np.float32 and lo.flags.c_contiguous))
+        ok = ok and (be is None or (be.shape == (B,) and be.dtype == np.int32 and be.flags.c_contiguous))
+        if not ok:
+            raise ValueError("out arrays must be C-contiguous first [2,B] f32, losses [S,B] f32, best [B] i32")
+        ps = p.c_struct()
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = N.lib.ocd_solve_first_host(self._h, C.addressof(ps), vp(world), vp(oc), Bo, vp(weights), Bw, vp(idx),
+                                        vp(cs), vp(first), vp(lo), vp(be), B)
+        N.check(rc, "ocd_solve_first_host")
+        return out
 
     def episodes_soa(self, p: PlannerParams, sc: Scenario, robot_init: np.ndarray, plan_weights: np.ndarray,
                      true_weights: np.ndarray, T: int, weight_idx=None, other_init=None, unlucky_idx=None,
