@@ -14,8 +14,12 @@ Extra keys on the JSON line: roofline (FP32-pipe bound; the peak is measured in 
 dependent-free FMA kernel, since MEASURED_PEAKS.json has no FP32 figure), hbm (algorithmic bytes
 vs the measured copy bandwidth, to show the path is nowhere near memory-bound), e2e (same metric
 through the host-buffer C ABI, copies inside), cpu_baseline (the CPU oracle on this box's cores),
-cmaes (candidate-evals/s of the finite_horizon cmaes --n_inits 5 generation, one episode launch),
-horizons (solves/s at H = 15 and H = 50, the other horizons BASELINE's metric names).
+cmaes (candidate-evals/s of one CMA-ES generation of BASELINE configs[1..3]: finite_horizon n_inits 5, local_opt
+n_inits 10, replanning T=20 x 2 samples -- one episode launch each), cmaes_multi (64 independent CMA-ES runs per GPU in
+lock step: the axis on which candidate-evals/s scales with GPUs), horizons (solves/s at H = 15 and H = 50, the other
+horizons BASELINE's metric names), sweep (corner points of BASELINE configs[4]), e2e_first_control (the
+receding-horizon caller's host call: only plan[0] comes back), cpu_baseline_serial (the reference's own driving style:
+one problem at a time, one autograd call per SGD step, one thread).
 """
 from __future__ import annotations
 
@@ -36,12 +40,19 @@ SHAPE = dict(H=5, C=2, L=3, S=3, n_iter=100)
 METRIC, UNIT = "mpc_solves_per_sec", "solves/s"
 
 
-def _config(B, n_gpus):
-    return {"workload": "synthetic sweep (BASELINE configs[4]) at the finite_horizon shape: "
-                        f"{B} independent MPC problems per GPU, H=5, 2 cars, 3 lanes, 3 starts x 100 SGD iterations",
-            "problems_per_gpu": B, "n_gpus": n_gpus, "horizon": 5, "cars": 2, "lanes": 3, "starts": 3,
-            "n_iter": 100, "lr": 0.1, "inits_per_candidate": 5, "parallelism": f"problem-sharded x{n_gpus}",
-            "l2_policy": "4 rotating input/output sets (>= 350 MB in total, L2 is 126 MB)"}
+def _config(B, n_gpus, per_step=None):
+    """per_step: problems one step actually solves when that is a bounded sample of the workload (the CPU arm)."""
+    cfg = {"workload": "synthetic sweep (BASELINE configs[4]) at the finite_horizon shape: independent MPC problems, "
+                       "H=5, 2 cars, 3 lanes, 3 starts x 100 SGD iterations",
+           "problems_per_gpu": B, "n_gpus": n_gpus, "horizon": 5, "cars": 2, "lanes": 3, "starts": 3,
+           "n_iter": 100, "lr": 0.1, "inits_per_candidate": 5, "parallelism": f"problem-sharded x{n_gpus}",
+           "l2_policy": "4 rotating input/output sets (>= 350 MB in total, L2 is 126 MB)"}
+    if per_step is not None:
+        cfg["problems_per_step"] = per_step
+        cfg["sample_note"] = (f"the CPU arm solves a bounded sample of {per_step} problems of this workload per step on the "
+                              f"host, not {B} per GPU; solves/s is a rate, so the two arms compare directly")
+        cfg["l2_policy"] = "n/a (host)"
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------
@@ -116,7 +127,7 @@ def cpu_arm(problems: int, threads: int | None = None, seed: int = 1234):
     """Times the CPU oracle (oracle/: C restatement of the reference's planner, OpenMP over
     problems) on `problems` synthetic problems of the bench shape.  -> (solves/s, seconds, threads)"""
     import oracle as O
-    from l4dc_mpc_ocd_b200 import synthetic
+    from l4dc_mpc_ocd_b200 import synthetic       # plain numpy; the package loads libocd_b200.so only when the engine is used
     threads = threads or host_threads()
     batch = synthetic.make_batch(problems, seed=seed)
     w = batch["weights"][batch["weight_idx"]]
@@ -143,7 +154,7 @@ def reference_main(args, rank: int, world_size: int):
         _, dt, _ = cpu_arm(per_step, threads, seed=1234 + i)
         t_tot += dt
     value = per_step * args.steps / t_tot
-    cfg = _config(args.problems, args.gpus)
+    cfg = _config(args.problems, args.gpus, per_step=per_step)
     sample = f"{per_step} synthetic problems of the bench shape per step x {args.steps} steps"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -184,6 +195,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from l4dc_mpc_ocd_b200 import parallel
+    # one process per GPU on one host: each rank takes its own slice of the host's cores (copy threads, pinned buffers)
+    cpus_owned = parallel.bind_rank_cpus(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world_size)))
     distributed = world_size > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -262,9 +276,12 @@ def main():
                 "frac": achieved_tf / (fp32_peak / 1e12), "traffic": traffic,
                 "bound_note": "BASELINE's north_star names the FP32 pipe as this path's roofline: no stage is a dense "
                               "contraction (no tensor roofline) and HBM carries 0.3 % of its measured bandwidth (see hbm)",
-                "peak_source": "dependent-free FFMA kernel measured in this job (MEASURED_PEAKS.json has no FP32 figure)",
+                "peak_source": "dependent-free FFMA kernel (512 FMAs per loop trip) measured in this job; "
+                               "MEASURED_PEAKS.json has no FP32 figure; nominal = 148 SMs x 128 lanes x 2 x sm_max_mhz",
                 "nominal_peak": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
-                "flops_per_solve": flops, "kernel": "k_solve<5,1,3,fast,wide>", "kernel_ms": own_ms}
+                "flops_per_solve": flops, "kernel": f"k_solve<5,1,3,fast,{ocd.kernel_form(p, B)}>", "kernel_ms": own_ms,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set "
+                                  "full capture of this kernel at this batch size (not re-measured in this job)"}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm = {"achieved": hbm_bytes * B / (own_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
            "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback",
@@ -318,14 +335,41 @@ def main():
                        "api": "ocd_solve_batch_host: pinned host arrays in, pinned host arrays out, "
                               "ramped column chunks over an H2D stream, two compute lanes and a D2H stream, so copies overlap the solve",
                        "pageable_host_arrays_value": B * world_size / t_pageable}
+        # the receding-horizon caller's call (ocd_solve_first_host): same inputs, only plan[0] + losses + winner come back
+        f_out = dict(first=ocd.HostContext.pinned_empty((2, B)), losses=h_out["losses"], best=h_out["best"])
+        for _ in range(2):
+            ctx.solve_first_soa(p, h_world, h_w, weight_idx=h_idx, out=f_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            ctx.solve_first_soa(p, h_world, h_w, weight_idx=h_idx, out=f_out)
+        t_first = max_over_ranks(time.perf_counter() - t0)
+        line["e2e_first_control"] = {
+            "value": B * ke * world_size / t_first, "unit": UNIT, "ms_per_step": 1e3 * t_first / ke,
+            "h2d_bytes_per_step": line["e2e"]["h2d_bytes_per_step"],
+            "d2h_bytes_per_step": int(f_out["first"].nbytes + f_out["losses"].nbytes + f_out["best"].nbytes),
+            "api": "ocd_solve_first_host: what PlannerCar._get_next_control needs -- plan[0], losses, winner"}
+        line["e2e"]["host_cpus_per_rank"] = cpus_owned
         line["gpu_launches"] = launches
         ctx.close()
 
         # ---- candidate-evals/s: one CMA-ES generation of finite_horizon cmaes --n_inits 5 -------------
-        line["cmaes"] = cmaes_leg(eng, ocd, dist if distributed else None, rank, world_size, max_over_ranks, barrier)
+        dd = dist if distributed else None
+        line["cmaes"] = cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "finite_horizon", 5)
+        line["cmaes_configs"] = [line["cmaes"],
+                                 cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "local_opt", 10),
+                                 cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "replanning", 5)]
+        # independent CMA-ES runs in lock step: 64 runs per GPU (weak), and a fixed 512 runs over all GPUs (strong)
+        line["cmaes_multi"] = cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "finite_horizon", 5,
+                                        runs=64 * world_size)
+        line["cmaes_multi_strong"] = cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "finite_horizon",
+                                               5, runs=512)
 
         # ---- the other horizons of the metric (H = 5..50): two points of BASELINE configs[4] -------------------
-        line["horizons"] = horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak)
+        line["horizons"] = horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak,
+                                        nominal_tf * 1e12)
+        # ---- BASELINE configs[4]: corner points of the sweep (all of it: scripts/sweep.py -> profiles/) ----------
+        line["sweep"] = sweep_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, nominal_tf * 1e12)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------
     if not args.no_extras and world_size == 1:
@@ -335,77 +379,117 @@ def main():
         v, dt, _ = cpu_arm(n, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n} problems of the bench shape, oracle C port with OpenMP, {dt:.1f} s"}
+        # the reference's own driving style (cpu_ref_serial): one problem at a time, a Python
+        # loop with one autograd call per SGD step, one thread -- torch-CPU standing in for TensorFlow
+        from oracle import torch_serial
+        vs, dts = torch_serial.time_serial_solves(2)
+        line["cpu_baseline_serial"] = {"value": vs, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "sample": f"2 problems of the bench shape, float32 torch-CPU autograd restatement "
+                                                 f"driven like the reference (one tape per SGD step), {dts:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
 
 
-def horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak):
-    """H = 15 and H = 50 (2 cars, the sweep's learning rates), device-resident, a few launches each: the
-    segmented-adjoint kernels.  Same accounting as the headline: all ranks' solves / slowest rank's time."""
+SWEEP_LR = {5: 0.1, 15: 0.02, 50: 0.0003}     # the reference's lr = 0.1 is only stable at its own H = 5 / 6
+
+
+def _timed_solve(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, H, C, B, reps):
+    """One sweep point, device-resident: -> (ms per launch as the max over ranks, all losses finite)."""
     import torch
+    p = ocd.PlannerParams(H=H, C=C, lr=SWEEP_LR.get(H, 0.1))
+    b = synthetic.make_batch(B, C=C, seed=99 + rank)
+    world = torch.as_tensor(b["world"], device=eng.device).permute(1, 2, 0).contiguous()
+    w = torch.as_tensor(b["weights"], device=eng.device).t().contiguous()
+    idx = torch.as_tensor(b["weight_idx"], device=eng.device)
+    out = eng.solve_soa(p, world, w, w.shape[1], idx)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.solve_soa(p, world, w, w.shape[1], idx, out=out)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(float(e0.elapsed_time(e1))) / reps
+    finite = bool(torch.isfinite(out["losses"]).all().item())
+    return p, ms, finite
+
+
+def horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, fp32_peak, nominal):
+    """H = 15 and H = 50 (2 cars, the sweep's learning rates), device-resident, a few launches each: the
+    medium-horizon (Q) and long-horizon (segmented) kernels.  Same accounting as the headline: all ranks'
+    solves / slowest rank's time."""
     rows = []
-    for H, B, lr in ((15, 262144, 0.03), (50, 65536, 0.003)):
-        p = ocd.PlannerParams(H=H, C=2, lr=lr)
-        b = synthetic.make_batch(B, seed=99 + rank)
-        world = torch.as_tensor(b["world"], device=eng.device).permute(1, 2, 0).contiguous()
-        w = torch.as_tensor(b["weights"], device=eng.device).t().contiguous()
-        idx = torch.as_tensor(b["weight_idx"], device=eng.device)
-        out = eng.solve_soa(p, world, w, w.shape[1], idx)
-        barrier()
-        reps = 5
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            eng.solve_soa(p, world, w, w.shape[1], idx, out=out)
-        e1.record()
-        barrier()
-        ms = max_over_ranks(float(e0.elapsed_time(e1))) / reps
+    for H, B in ((15, 262144), (50, 65536)):
+        p, ms, finite = _timed_solve(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, H, 2, B, 5)
         fl = synthetic.flops_per_solve(H, 2, 3)
-        rows.append({"horizon": H, "problems_per_gpu": B, "lr": lr, "ms_per_launch": ms,
-                     "solves_per_sec": B * world_size / (ms * 1e-3),
-                     "frac_of_measured_fp32": fl * B / (ms * 1e-3) / fp32_peak})
+        rows.append({"horizon": H, "problems_per_gpu": B, "lr": p.lr, "ms_per_launch": ms,
+                     "solves_per_sec": B * world_size / (ms * 1e-3), "kernel_form": ocd.kernel_form(p, B),
+                     "frac_of_measured_fp32": fl * B / (ms * 1e-3) / fp32_peak,
+                     "frac_of_nominal_fp32": fl * B / (ms * 1e-3) / nominal, "all_losses_finite": finite})
     return rows
 
 
-def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier):
-    """BASELINE configs[1]: finite_horizon cmaes --n_inits 5.  One generation = popsize 9 candidates
-    x 5 initial states x 15 control steps, evaluated by ONE ocd_episode_batch launch; with N ranks
-    the 45 episodes are sharded and the per-episode returns all-gathered (NCCL)."""
+def sweep_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, nominal):
+    """Corner points of BASELINE configs[4] (4K..1M problems x H 5/15/50 x 2..6 cars), per GPU, all ranks at once."""
+    rows = []
+    for H in (5, 15, 50):
+        for C in (2, 6):
+            for B in (4096, 1048576):
+                reps = 2 if H * B >= 15 * 1048576 else 5
+                p, ms, finite = _timed_solve(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, H, C, B, reps)
+                fl = synthetic.flops_per_solve(H, C, 3)
+                rows.append({"H": H, "C": C, "B_per_gpu": B, "lr": p.lr, "ms": round(ms, 4),
+                             "solves_per_sec": B * world_size / (ms * 1e-3), "form": ocd.kernel_form(p, B),
+                             "frac_of_nominal_fp32": round(fl * B / (ms * 1e-3) / nominal, 4), "finite": finite})
+    return rows
+
+
+def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier, scenario, n_inits, runs=1):
+    """BASELINE configs[1..3]: one CMA-ES generation of `run_mpc_ord.py <scenario> cmaes --n_inits n` = popsize 9
+    candidates x n_inits initial states x samples episodes of T control steps, evaluated by ONE ocd_episode_batch
+    launch; with N ranks the episodes are sharded and the per-episode returns all-gathered (NCCL).
+    runs > 1: that many INDEPENDENT CMA-ES runs (different init groups, `--one_by_one` / the n_inits x seeds study of
+    generalization_data.py) advanced in lock step -- their generations share the launch."""
     import torch
-    pop, n_inits, T = 9, 5, 15
+    from l4dc_mpc_ocd_b200.batched import compile_world, unlucky_sequence
+    from l4dc_mpc_ocd_b200.experiments import run_mpc_ord
+    env = run_mpc_ord.envs[scenario]
+    T, ns = env["eval_horizon"], env["num_eval_samples"]
+    car, world, inits = env["make_env"](env_seeds=[(1000000 + i) % (2 ** 32) for i in range(n_inits * runs)], debug=False)
+    prog = compile_world(world, car)
+    p, sc = prog.params, prog.scenario
+    pop = 9                                               # pycma: 4 + floor(3 ln K), K = 7 or 6
     rng = np.random.default_rng(2024)
-    w_true = np.array([-5, 0., 0., 0., -6., -50, -50])
+    w_true = np.asarray(car.weights, np.float64)
     w_true = (w_true / np.linalg.norm(w_true)).astype(np.float32)
-    cand = w_true[None] + 0.05 * rng.normal(size=(pop, 7))
+    cand = w_true[None] + 0.05 * rng.normal(size=(runs * pop, p.K))
     cand = (cand / np.linalg.norm(cand, axis=1, keepdims=True)).astype(np.float32)
-    inits = np.stack([rng.uniform(-0.1, 0.1, n_inits), rng.uniform(-0.95, -0.85, n_inits),
-                      rng.uniform(0.7, 0.9, n_inits), np.full(n_inits, np.pi / 2)], 1).astype(np.float32)
-    ri = np.tile(inits, (pop, 1))
-    widx = np.repeat(np.arange(pop), n_inits).astype(np.int32)
-    B = pop * n_inits
+    I = np.asarray(inits, np.float32).reshape(runs, n_inits, 4)
+    # episode (run r, candidate c, init i, sample s), flattened in that order
+    ri = np.repeat(np.tile(I[:, None], (1, pop, 1, 1)).reshape(-1, 4), ns, axis=0)
+    widx = np.repeat(np.arange(runs * pop, dtype=np.int32), n_inits * ns)
+    B = ri.shape[0]
+    ul = np.asarray(unlucky_sequence(world, B), np.int32) if prog.replanning else None
     per = (B + world_size - 1) // world_size
-    lo, hi = rank * per, min(B, (rank + 1) * per)
-    p = ocd.PlannerParams()
-    sc = ocd.Scenario(init_state=[[0.0, -0.6, 0.5, np.pi / 2]], kind=[0], friction=[0.0], control=[[0.0, 0.0]])
     dev = eng.device
-    # shard padded to `per` problems so the all-gather is regular
-    sel = np.arange(lo, lo + per) % B
+    sel = np.minimum(np.arange(rank * per, rank * per + per), B - 1)     # shard padded to `per` episodes: regular all-gather
     ris = torch.as_tensor(np.ascontiguousarray(ri[sel].T), device=dev)
     w = torch.as_tensor(np.ascontiguousarray(cand.T), device=dev)
     idx = torch.as_tensor(widx[sel], device=dev)
+    uls = None if ul is None else torch.as_tensor(ul[sel], device=dev)
     tw = torch.as_tensor(w_true, device=dev)
     out = dict(returns=torch.empty((per,), dtype=torch.float32, device=dev))
     gathered = torch.empty((per * world_size,), dtype=torch.float32, device=dev)
 
     def generation():
-        eng.episodes_soa(p, sc, ris, w, pop, tw, T, weight_idx=idx, out=out)
+        eng.episodes_soa(p, sc, ris, w, runs * pop, tw, T, weight_idx=idx, unlucky_idx=uls, out=out)
         if dist is not None:
             dist.all_gather_into_tensor(gathered, out["returns"])
         else:
             gathered.copy_(out["returns"])
-        return gathered[:B].reshape(pop, n_inits).sum(1)
+        return gathered[:B].reshape(runs * pop, n_inits * ns).sum(1) / ns
 
     for _ in range(3):
         generation()
@@ -418,9 +502,10 @@ def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier):
     e1.record()
     barrier()
     ms = max_over_ranks(float(e0.elapsed_time(e1))) / reps
-    return {"workload": "finite_horizon cmaes --n_inits 5: one generation = 9 candidates x 5 inits x 15 control steps",
-            "candidate_evals_per_sec": pop / (ms * 1e-3), "ms_per_generation": ms,
-            "mpc_solves_per_generation": B * T, "episodes_per_rank": per,
+    return {"workload": f"{scenario} cmaes --n_inits {n_inits}: one generation = {runs} run(s) x 9 candidates x {n_inits} inits x "
+                        f"{ns} sample(s) x {T} control steps",
+            "candidate_evals_per_sec": runs * pop / (ms * 1e-3), "ms_per_generation": ms, "runs": runs,
+            "mpc_solves_per_generation": B * T, "episodes_per_rank": per, "kernel_form": ocd.kernel_form(p, per, True),
             "collective": "all_gather of per-episode returns (NCCL)" if dist is not None else "none (1 GPU)",
             "first_candidate_return": float(cand_returns[0].item())}
 

@@ -108,3 +108,25 @@ def fmin2(objective: Callable, x0, sigma0, options: Optional[dict] = None, batch
         fit = batch_objective(pop) if batch_objective is not None else [objective(list(x)) for x in pop]
         es.tell(fit)
     return es.best_x, es
+
+
+def fmin2_lockstep(batch_objective_multi: Callable, x0s, sigma0, options_list):
+    """R independent `fmin2` runs advanced in lock step.  `batch_objective_multi(pops)` gets one population per run
+    (an empty list for a run that has stopped) and returns one fitness array per run -- so that all runs' generations
+    can be evaluated in one launch.  Each run draws from its own RandomState, asks, tells and stops exactly as it
+    would alone.  -> [(xbest, es)] per run."""
+    runs = []
+    for x0, opt in zip(x0s, options_list):
+        opt = dict(opt or {})
+        es = CMAES(x0, sigma0, seed=opt.get("seed"), popsize=opt.get("popsize"))
+        runs.append((es, {k: opt[k] for k in ("maxfevals", "maxiter", "tolfun", "tolx") if k in opt}))
+    active = [i for i, (es, kw) in enumerate(runs) if es.stop(**kw) is None]
+    while active:
+        pops = [[] for _ in runs]
+        for i in active:
+            pops[i] = runs[i][0].ask()
+        fits = batch_objective_multi(pops)
+        for i in active:
+            runs[i][0].tell(fits[i])
+        active = [i for i in active if runs[i][0].stop(**runs[i][1]) is None]
+    return [(es.best_x, es) for es, _ in runs]

@@ -3,8 +3,8 @@
     python -m l4dc_mpc_ocd_b200.experiments.run_mpc_ord finite_horizon cmaes --n_inits 5
 
 Differences that follow from the engine: no multiprocessing.Pool (one process drives one GPU and a
-whole CMA-ES generation is one kernel launch; `--one_by_one` runs its per-init optimisations one
-after the other), `vis` prints the returns of the true and the tuned weights instead of rendering,
+whole CMA-ES generation is one kernel launch; the per-init CMA-ES runs of `--one_by_one`, one worker
+process each in the reference, advance in lock step and share one launch per generation), `vis` prints the returns of the true and the tuned weights instead of rendering,
 and `--max_evals` bounds the CMA-ES run (the reference runs until pycma's own termination).  Under
 torchrun (WORLD_SIZE > 1) the episodes of every generation are sharded over the ranks and the
 per-episode returns all-gathered (see l4dc_mpc_ocd_b200.parallel)."""
@@ -14,7 +14,7 @@ from argparse import ArgumentParser
 
 import numpy as np
 
-from ..interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env
+from ..interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env, optimize_cmaes_lockstep
 from .local_opt_scenario import local_opt_env
 from .replanning_world import setup_world as replanning_env
 
@@ -48,16 +48,21 @@ envs = {
 }
 
 
-def run_opt(env, init_states, args, optimization_seed, verbose=True):
-    """One optimisation over `init_states` (reference run_opt, :92-122).  Returns the MPC_ORD."""
+def make_ord(env, init_states, args, optimization_seed, verbose=True):
+    """The MPC_ORD of one optimisation over `init_states` (first half of the reference's run_opt, :92-104)."""
     if verbose:
         print("OPTIMIZING REWARD FROM INIT STATES", init_states)
     car, world, _ = env['make_env'](debug=True)
     tag = args.n_inits if not args.one_by_one else fmt(init_states[0])
     save_path = (f'{args.optimizer}_{args.scenario}__designer_weights_{fmt(car.weights)}__{tag}_init_seed_{args.seed}'
                  f'_opt_seed_{optimization_seed}_sigma_{args.sigma}.pkl') if not args.no_save else None
-    mpc_ord = MPC_ORD(world, car, init_states, env['eval_horizon'], num_samples=env['num_eval_samples'],
-                      save_path=save_path, verbose=verbose)
+    return MPC_ORD(world, car, init_states, env['eval_horizon'], num_samples=env['num_eval_samples'],
+                   save_path=save_path, verbose=verbose), car
+
+
+def run_opt(env, init_states, args, optimization_seed, verbose=True):
+    """One optimisation over `init_states` (reference run_opt, :92-122).  Returns the MPC_ORD."""
+    mpc_ord, car = make_ord(env, init_states, args, optimization_seed, verbose)
     if args.optimizer == 'random':
         mpc_ord.optimize_random_search(n_iter=400, seed=optimization_seed)
     elif args.optimizer == 'vis':
@@ -73,6 +78,16 @@ def run_opt(env, init_states, args, optimization_seed, verbose=True):
     return mpc_ord
 
 
+def run_opts_lockstep(env, groups, args, optimization_seed, verbose=True):
+    """`--one_by_one` with CMA-ES: the reference gives every init group its own worker process
+    (`Pool(len(init_states_groups))`, :83-90); here the groups' CMA-ES runs advance in lock step and generation g of
+    all of them is one episode launch (sharded over the ranks under torchrun).  Returns the MPC_ORDs."""
+    ords = [make_ord(env, g, args, optimization_seed, verbose)[0] for g in groups]
+    stop = {} if args.max_evals is None else dict(maxfevals=args.max_evals)
+    optimize_cmaes_lockstep(ords, [optimization_seed] * len(ords), sigma0=args.sigma, **stop)
+    return ords
+
+
 def _init_distributed():
     """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL process group.  -> rank or None."""
     import os
@@ -81,7 +96,9 @@ def _init_distributed():
     import torch
     import torch.distributed as dist
     from ..runtime import set_default_device
+    from ..parallel import bind_rank_cpus
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_rank_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
     torch.cuda.set_device(local)
     set_default_device(local)
     if not dist.is_initialized():
@@ -132,6 +149,8 @@ def main(argv=None):
     groups = [[s] for s in init_states] if args.one_by_one else [init_states]
     if not args.quiet:
         print('init_states:', groups)
+    if args.optimizer == 'cmaes' and len(groups) > 1:
+        return run_opts_lockstep(env, groups, args, optimization_seed, verbose=not args.quiet)
     return [run_opt(env, g, args, optimization_seed, verbose=not args.quiet) for g in groups]
 
 

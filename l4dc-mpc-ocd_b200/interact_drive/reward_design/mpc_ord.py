@@ -47,6 +47,104 @@ def sample_init_state(env_seed, x, y, speed):
     return np.array([_truncnorm_sample(*x), _truncnorm_sample(*y), _truncnorm_sample(*speed), np.pi / 2])
 
 
+def _launch_sharded(eng, ord_, W, robot, widx, unlucky):
+    """One process per GPU: this rank runs its contiguous shard of the episodes, then the per-episode rows -- return
+    and final world state -- are all-gathered (the path's only exchange step), so every rank holds the same data and
+    leaves the same Python-object state behind as a single-GPU run.  -> (returns [B], final world [C, 4] of the
+    last episode), host arrays."""
+    p, B = ord_.program.params, robot.shape[0]
+
+    def run(idx):
+        o = eng.episodes(p, ord_.program.scenario, robot[idx], W, as_f32(ord_.designer_weights), ord_.designer_horizon,
+                         weight_idx=widx[idx], unlucky_idx=None if unlucky is None else unlucky[idx], final_world=True)
+        import torch
+        return torch.cat([o["returns"][:, None], o["final_world"].reshape(len(idx), -1)], dim=1)
+
+    rows = _par.sharded_rows(run, B).cpu().numpy()
+    return np.ascontiguousarray(rows[:, 0]), rows[-1, 1:].reshape(p.C, 4)
+
+
+def eval_weights_lockstep(runs: Sequence["MPC_ORD"], weight_lists: Sequence[Sequence]) -> list:
+    """`eval_weights_batch` for several independent MPC_ORDs in ONE launch: run r evaluates weight_lists[r] (possibly
+    empty) on ITS initial states.  The reference runs such optimisations in separate worker processes
+    (`Pool(len(init_states_groups))`, experiments/run_mpc_ord.py:83-90); here their generations share a kernel launch
+    -- sharded over the ranks when a process group is up -- and every run's history advances exactly as if it had
+    been evaluated alone (each episode's result does not depend on what else is in the batch).
+    -> list of -totals arrays, one per run."""
+    runs = list(runs)
+    ref = runs[0]
+    sig = (bytes(ref.program.params.c_struct()), bytes(ref.program.scenario.c_struct()), ref.designer_horizon,
+           ref.num_samples, as_f32(ref.designer_weights).tobytes())
+    for r in runs[1:]:
+        if (bytes(r.program.params.c_struct()), bytes(r.program.scenario.c_struct()), r.designer_horizon,
+                r.num_samples, as_f32(r.designer_weights).tobytes()) != sig:
+            raise ValueError("eval_weights_lockstep: the runs must share scenario, planner and designer weights")
+    lists = [[np.asarray(w, dtype=np.float64) for w in wl] for wl in weight_lists]
+    lists = [[w[0] if w.ndim == 2 else w for w in wl] for wl in lists]
+    active = [i for i, wl in enumerate(lists) if len(wl)]
+    if not active:
+        return [np.zeros(0) for _ in runs]
+    batches = {i: runs[i]._episode_batch(lists[i]) for i in active}
+    off, Ws, robots, widxs, uls = 0, [], [], [], []
+    for i in active:
+        b = batches[i]
+        Ws.append(b["W"]); robots.append(b["robot"]); widxs.append(b["widx"] + off)
+        uls.append(b["unlucky"])
+        off += b["W"].shape[0]
+    W, robot, widx = np.concatenate(Ws), np.concatenate(robots), np.concatenate(widxs).astype(np.int32)
+    unlucky = None if uls[0] is None else np.concatenate(uls).astype(np.int32)
+    eng = get_engine(ref._device)
+    p = ref.program.params
+    if _par.world()[1] > 1:
+        import torch
+        B = robot.shape[0]
+
+        def run(idx):
+            o = eng.episodes(p, ref.program.scenario, robot[idx], W, as_f32(ref.designer_weights), ref.designer_horizon,
+                             weight_idx=widx[idx], unlucky_idx=None if unlucky is None else unlucky[idx],
+                             final_world=True)
+            return torch.cat([o["returns"][:, None], o["final_world"].reshape(len(idx), -1)], dim=1)
+
+        rows = _par.sharded_rows(run, B).cpu().numpy()
+    else:
+        import torch
+        o = eng.episodes(p, ref.program.scenario, robot, W, as_f32(ref.designer_weights), ref.designer_horizon,
+                         weight_idx=widx, unlucky_idx=unlucky, final_world=True)
+        rows = torch.cat([o["returns"][:, None], o["final_world"].reshape(robot.shape[0], -1)], dim=1).cpu().numpy()
+    ref.kernel_launches += 1
+    out, at = [np.zeros(0) for _ in runs], 0
+    for i in active:
+        b = batches[i]
+        n = b["robot"].shape[0]
+        part = rows[at:at + n]
+        at += n
+        runs[i]._after_episodes(b, part[-1, 1:].reshape(p.C, 4))
+        out[i] = runs[i]._record(lists[i], np.ascontiguousarray(part[:, 0]).reshape(b["shape"]))
+    return out
+
+
+def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sigma0=0.1, **stop) -> list:
+    """R independent `optimize_cmaes` runs (reference :33-45, one worker process each in the reference) advanced in
+    lock step: generation g of every run that is still going is ONE episode launch.  Run r uses seeds[r]; its
+    candidates, history and result are those of `runs[r].optimize_cmaes(seed=seeds[r], ...)` run alone.
+    -> list of best weight vectors."""
+    runs = list(runs)
+    assert len(seeds) == len(runs)
+    for r, seed in zip(runs, seeds):
+        assert seed != 0
+        assert not r.done
+        r.history.seed = seed
+        r.should_save_history = True
+    eval_weights_lockstep(runs, [[r.designer_weights] for r in runs])
+    res = _cma.fmin2_lockstep(lambda pops: eval_weights_lockstep(runs, pops),
+                              [list(r.designer_weights) for r in runs], sigma0,
+                              [dict(seed=seed, **stop) for seed in seeds])
+    for r in runs:
+        r.should_save_history = False
+        r.done = True
+    return [x for x, _ in res]
+
+
 class MPC_ORD:
     """Evaluates / optimises surrogate reward weights for a planning car by the TRUE-weight return of
     the receding-horizon episodes it produces."""
@@ -83,10 +181,10 @@ class MPC_ORD:
             w = w / np.linalg.norm(w)
         return w.astype(np.float32)
 
-    def episode_returns(self, weight_matrix, inits: Optional[Sequence] = None, trace: bool = False):
-        """weight_matrix [n_cand, K] (raw candidates) x inits [n_init, 4] x num_samples ->
-        returns [n_cand, n_init, num_samples] of sum_t true_w . features(past_state_t), one launch.
-        With trace=True also the per-step controls/states of every episode (host arrays)."""
+    def _episode_batch(self, weight_matrix, inits: Optional[Sequence] = None) -> dict:
+        """The flat episode batch of `weight_matrix` [n_cand, K] (raw candidates) x inits [n_init, 4] x num_samples:
+        planning weights W [nc, K], robot states [nc*ni*ns, 4], the candidate of every episode and -- replanning world --
+        the car that vanishes in it.  Advances the world's own reset toggle like the serial loops would."""
         W = np.stack([self._planning_weights(w) for w in np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))])
         inits = self.init_car_states if inits is None else inits
         I = np.stack([as_f32(s, (4,)) for s in inits])
@@ -95,44 +193,43 @@ class MPC_ORD:
         widx = np.repeat(np.arange(nc, dtype=np.int32), ni * ns)
         unlucky = None
         if self.program.replanning:
-            # every evaluation of one init resets the world num_samples times (reference :87-89); all
-            # candidates see the same toggle sequence as a serial run would give the first of them
-            seq = unlucky_sequence(self.world, ni * ns)
-            unlucky = np.tile(np.asarray(seq, np.int32), nc)
+            # the reference resets the world once per (candidate, init, sample), serially, and every reset toggles the
+            # vanishing car (reference :87-89, replanning_world.py:19-27): the sequence runs over all nc*ni*ns resets
+            unlucky = np.asarray(unlucky_sequence(self.world, nc * ni * ns), np.int32)
+        return dict(W=W, I=I, robot=robot, widx=widx, unlucky=unlucky, shape=(nc, ni, ns))
+
+    def _after_episodes(self, batch: dict, final_world: np.ndarray) -> None:
+        """Leave the Python objects the way a serial evaluation would: last weights, last init, final state."""
+        self.car.weights = batch["W"][-1]
+        self.car.init_state = batch["I"][-1]
+        for c, st in zip(self.world.cars, final_world):
+            c.state = st
+
+    def episode_returns(self, weight_matrix, inits: Optional[Sequence] = None, trace: bool = False):
+        """weight_matrix [n_cand, K] (raw candidates) x inits [n_init, 4] x num_samples ->
+        returns [n_cand, n_init, num_samples] of sum_t true_w . features(past_state_t), one launch.
+        With trace=True also the per-step controls/states of every episode (host arrays)."""
+        batch = self._episode_batch(weight_matrix, inits)
+        W, robot, widx, unlucky = batch["W"], batch["robot"], batch["widx"], batch["unlucky"]
         eng = get_engine(self._device)
-        B = robot.shape[0]
         rank, ws = _par.world()
+        out = None
         if ws > 1 and not trace:
-            # one process per GPU: this rank runs its contiguous shard of the episodes, then the
-            # per-episode returns are all-gathered (the path's only exchange step)
-            def run(idx):
-                o = eng.episodes(self.program.params, self.program.scenario, robot[idx], W,
-                                 as_f32(self.designer_weights), self.designer_horizon, weight_idx=widx[idx],
-                                 unlucky_idx=None if unlucky is None else unlucky[idx], final_world=True)
-                run.final = o["final_world"]
-                return o["returns"]
-            returns = _par.sharded_returns(run, B)
-            out = dict(returns=returns, final_world=run.final)
+            ret_flat, final = _launch_sharded(eng, self, W, robot, widx, unlucky)
         elif not trace:
             # the CMA-ES hot loop: everything but the candidates is the same from one generation to the next, so
             # the device copies of the initial states / indices are kept, only W goes up and ONE buffer (returns +
             # final worlds) comes back
             ret_flat, final = self._episode_returns_cached(eng, W, robot, widx, unlucky)
-            out = None
         else:
             out = eng.episodes(self.program.params, self.program.scenario, robot, W, as_f32(self.designer_weights),
                                self.designer_horizon, weight_idx=widx, unlucky_idx=unlucky, trace=trace,
                                final_world=True)
-        self.kernel_launches += 1
-        if out is not None:
             ret_flat = out["returns"].cpu().numpy()
             final = out["final_world"].cpu().numpy()[-1]
-        ret = ret_flat.reshape(nc, ni, ns)
-        # leave the Python objects the way a serial evaluation would: last weights, last init, final state
-        self.car.weights = W[-1]
-        self.car.init_state = I[-1]
-        for c, s in zip(self.world.cars, final):
-            c.state = s
+        self.kernel_launches += 1
+        self._after_episodes(batch, final)
+        ret = ret_flat.reshape(batch["shape"])
         if trace:
             return ret, {k: out[k].cpu().numpy() for k in ("controls", "best", "states")}
         return ret
@@ -143,7 +240,8 @@ class MPC_ORD:
         import torch
         p, sc = self.program.params, self.program.scenario
         B, dev = robot.shape[0], eng.device
-        key = (robot.tobytes(), widx.tobytes(), None if unlucky is None else unlucky.tobytes(), str(dev))
+        key = (robot.tobytes(), widx.tobytes(), None if unlucky is None else unlucky.tobytes(), str(dev),
+               as_f32(self.designer_weights).tobytes())
         c = self._dev_cache.get(key)
         if c is None:
             if len(self._dev_cache) >= 8:
@@ -189,7 +287,11 @@ class MPC_ORD:
         advance exactly as if the rows had been evaluated one after the other."""
         W = [np.asarray(w, dtype=np.float64) for w in weight_matrix]
         W = [w[0] if w.ndim == 2 else w for w in W]
-        ret = self.episode_returns(W)                                 # [nc, ni, ns]
+        return self._record(W, self.episode_returns(W))               # [nc, ni, ns]
+
+    def _record(self, W, ret) -> np.ndarray:
+        """History / iteration bookkeeping of eval_weights (reference :128-151) for the candidates W with episode
+        returns ret [nc, ni, ns].  -> -totals."""
         totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
         for w, total in zip(W, totals):
             wn = w / np.linalg.norm(w)

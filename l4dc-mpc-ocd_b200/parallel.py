@@ -58,3 +58,41 @@ def sharded_returns(evaluate: Callable[[np.ndarray], torch.Tensor], B: int) -> t
     rank, ws = world()
     idx = shard_indices(B, rank, ws)
     return gather_returns(evaluate(idx), B)
+
+
+def gather_rows(local: torch.Tensor, B: int) -> torch.Tensor:
+    """local [per, F] on every rank -> the first B rows of the rank-ordered concatenation (every rank gets all)."""
+    rank, ws = world()
+    if ws == 1:
+        return local[:B]
+    flat = gather_returns(local.contiguous().reshape(-1), B * local.shape[1])
+    return flat.reshape(B, local.shape[1])
+
+
+def sharded_rows(evaluate: Callable[[np.ndarray], torch.Tensor], B: int) -> torch.Tensor:
+    """Like sharded_returns for `evaluate(indices) -> [len(indices), F]`: per-episode rows (return and final world
+    state), so that every rank ends with the same data and leaves the same Python-object state behind."""
+    rank, ws = world()
+    idx = shard_indices(B, rank, ws)
+    return gather_rows(evaluate(idx), B)
+
+
+def bind_rank_cpus(local_rank: int, local_world_size: int) -> int:
+    """One process per GPU on one host: give this rank its own contiguous slice of the CPUs the process may run
+    on (sched_setaffinity), so that the ranks' staging-copy threads and pinned buffers do not fight over the same
+    cores (the engine sizes its copy pool from the affinity mask).  Returns the number of CPUs this rank owns.
+    No-op when there is one rank, fewer CPUs than ranks, or no affinity support."""
+    import os
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+    if local_world_size <= 1 or len(cpus) < local_world_size:
+        return len(cpus)
+    per = len(cpus) // local_world_size
+    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return len(cpus)
+    return len(mine)

@@ -38,6 +38,42 @@ def _rel(a, b, floor=1e-6):
                         np.maximum(np.abs(np.asarray(b, np.float64)), floor)))
 
 
+def solve_conditioning(op, world, w_full, oc=None):
+    """How reproducible is the REFERENCE on these problems?  Fixed-budget gradient ascent on a reward with min / max
+    kinks is an iterated map; on some problems the f32 and f64 oracles, or the f32 oracle under ulp-sized input noise,
+    already disagree.  -> (ref f32, ref f64, cond_u [B]: largest plan deviation over the probes, cond_l [B, S]: same for the
+    losses, relative)."""
+    B = world.shape[0]
+    ref = O.generate_plan_batch(op, world, w_full, other_controls=oc)
+    ref64 = O.generate_plan_batch(op, world.astype(np.float64), w_full.astype(np.float64),
+                                  other_controls=None if oc is None else oc.astype(np.float64), dtype=np.float64)
+    cond_u = np.abs(ref["plan"] - ref64["plan"]).reshape(B, -1).max(1)
+    cond_l = np.abs(ref["losses"] - ref64["losses"]) / np.maximum(1.0, np.abs(ref64["losses"]))
+    # the lane-min / car-max features make the gradient discontinuous: an iterate that crosses such a
+    # boundary one iteration earlier or later lands elsewhere.  Probe with ulp-sized input noise.
+    for col, eps in ((0, 3e-8), (0, -3e-8), (3, 2.4e-7), (3, -2.4e-7), (2, 1.2e-7), (2, -1.2e-7), (1, 1.2e-7)):
+        wp = world.copy()
+        wp[:, 0, col] += np.float32(eps)
+        refp = O.generate_plan_batch(op, wp, w_full, other_controls=oc)
+        cond_u = np.maximum(cond_u, np.abs(ref["plan"] - refp["plan"]).reshape(B, -1).max(1))
+        cond_l = np.maximum(cond_l, np.abs(ref["losses"] - refp["losses"]) / np.maximum(1.0, np.abs(ref["losses"])))
+    return ref, ref64, cond_u, cond_l
+
+
+def episode_conditioning(spec, ri, w_plan, w_true, T, ul=None):
+    """The same question for whole episodes: relative spread of the oracle's return over f32 / f64 / ulp-sized noise in
+    the robot's initial x and speed.  -> (ref f32 [B], spread [B])."""
+    ref = O.episode_batch(spec.params, spec.scenario, ri, w_plan, w_true, T, unlucky_idx=ul)
+    alts = [O.episode_batch(spec.params, spec.scenario, ri.astype(np.float64), w_plan.astype(np.float64),
+                            w_true.astype(np.float64), T, unlucky_idx=ul, dtype=np.float64)]
+    for col, eps in ((0, 3e-8), (0, -3e-8), (2, 1.2e-7), (2, -1.2e-7)):
+        rp = ri.copy()
+        rp[:, col] += np.float32(eps)
+        alts.append(O.episode_batch(spec.params, spec.scenario, rp, w_plan, w_true, T, unlucky_idx=ul))
+    spread = np.max([np.abs(a - ref) for a in alts], axis=0) / np.maximum(np.abs(ref), 1e-6)
+    return ref, spread
+
+
 # ---- P0 primitives ---------------------------------------------------------------------------
 def test_dynamics_known_answers(engine):
     g = load_golden("primitives.json")
@@ -177,7 +213,7 @@ def test_generate_plan_golden_scenarios(engine, mode, _n):
     (5, 2, 3, 0, False, 100, 0.1), (5, 3, 2, 1, False, 100, 0.1), (6, 2, 3, 0, False, 200, 0.1),
     (5, 2, 3, 0, True, 100, 0.1), (3, 4, 3, 0, False, 60, 0.1), (8, 2, 3, 0, False, 50, 0.1),
     (15, 3, 3, 1, False, 40, 0.01), (5, 5, 3, 0, False, 100, 0.1), (15, 2, 3, 0, False, 100, 0.03),
-    (50, 2, 3, 0, False, 20, 0.003), (50, 6, 3, 0, False, 10, 0.003),
+    (50, 2, 3, 0, False, 20, 0.0003), (50, 6, 3, 0, False, 10, 0.0003),
     # every compile-time car count of the sweep specialisations (k_solve<5|0, 2..5, 3, fast>)
     (5, 3, 3, 0, False, 100, 0.1), (5, 4, 3, 0, False, 100, 0.1), (5, 6, 3, 0, False, 100, 0.1),
     (15, 4, 3, 0, False, 40, 0.03), (15, 5, 3, 1, False, 40, 0.03), (15, 6, 3, 0, False, 40, 0.03)])
@@ -194,21 +230,13 @@ def test_generate_plan_random_vs_oracle(engine, mode, _n, H, C, lanes, other_mod
     op = O.OracleParams(H=H, C=C, lane_x=lane_x, n_iter=n_iter, num_lanes=lanes, other_mode=other_mode,
                         extra_inits=extra, target_speed=1.0 if lanes == 3 else 1.2, lr=lr)
     w_full = batch["weights"][batch["weight_idx"]]
-    ref = O.generate_plan_batch(op, batch["world"], w_full, other_controls=oc)
-    ref64 = O.generate_plan_batch(op, batch["world"].astype(np.float64), w_full.astype(np.float64),
-                                  other_controls=None if oc is None else oc.astype(np.float64), dtype=np.float64)
-    cond_u = np.abs(ref["plan"] - ref64["plan"]).reshape(B, -1).max(1)
-    cond_l = np.abs(ref["losses"] - ref64["losses"]) / np.maximum(1.0, np.abs(ref64["losses"]))
-    # the lane-min / car-max features make the gradient discontinuous: an iterate that crosses such a
-    # boundary one iteration earlier or later lands elsewhere.  Probe with ulp-sized input noise.
-    for col, eps in ((0, 3e-8), (0, -3e-8), (3, 2.4e-7), (3, -2.4e-7), (2, 1.2e-7), (2, -1.2e-7), (1, 1.2e-7)):
-        wp = batch["world"].copy()
-        wp[:, 0, col] += np.float32(eps)
-        refp = O.generate_plan_batch(op, wp, w_full, other_controls=oc)
-        cond_u = np.maximum(cond_u, np.abs(ref["plan"] - refp["plan"]).reshape(B, -1).max(1))
-        cond_l = np.maximum(cond_l, np.abs(ref["losses"] - refp["losses"]) / np.maximum(1.0, np.abs(ref["losses"])))
+    ref, ref64, cond_u, cond_l = solve_conditioning(op, batch["world"], w_full, oc)
     well = (cond_u < 1e-5) & (ref["best"] == ref64["best"]) & (cond_l.max(1) < (2e-6 if H < 15 else 1e-4))
-    assert well.mean() >= (0.2 if H >= 15 else 0.5), well.mean()
+    # the observed fraction per shape is tracked in tests/golden/well_fractions.json (it depends on the oracle alone);
+    # it may not drop by more than 0.05, and every one of these problems is checked below
+    want = load_golden("well_fractions.json")["fractions"][f"H{H}_C{C}_L{lanes}_om{other_mode}_x{int(extra)}_n{n_iter}"]
+    print(f"well-conditioned fraction H={H} C={C}: {well.mean():.4f} (tracked {want})")
+    assert well.mean() >= want - 0.05, (well.mean(), want)
     res = engine.solve(_pp(op, mode), batch["world"], batch["weights"], weight_idx=batch["weight_idx"],
                        other_controls=oc)
     res = {k: v.cpu().numpy() for k, v in res.items()}
@@ -420,13 +448,16 @@ def test_episode_full_size_properties(engine, name, monkeypatch):
         monkeypatch.delenv("OCD_KERNEL_FORM")
         same = forced["returns"] == full["returns"][:4000]
         assert same.float().mean().item() >= 0.995, (form, same.float().mean().item())
-    # oracle spot checks
-    sel = np.linspace(0, B - 1, 32).astype(np.int64)
+    # oracle spot checks: every episode whose return the reference reproduces (f32 / f64 / ulp noise agree to 1e-5) must be
+    # within BASELINE's 1e-3 relative; an episode may only miss it where the oracle's own probes spread
+    sel = np.linspace(0, B - 1, 128).astype(np.int64)
     got = full["returns"].cpu().numpy()[sel]
-    ref = np.array([O.episode(spec.params, spec.scenario, ri[i], cand[widx[i]], wt, T,
-                              unlucky_idx=0 if ul is None else int(ul[i]))["ret"] for i in sel])
+    ref, spread = episode_conditioning(spec, ri[sel], cand[widx[sel]], wt, T, None if ul is None else ul[sel])
     rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
-    assert np.mean(rel <= 1e-3) >= 0.9, rel
+    well = spread < 1e-5
+    assert well.mean() >= 0.7, well.mean()
+    assert np.all(rel[well] <= 1e-3), (rel[well].max(), np.nonzero(well & (rel > 1e-3))[0])
+    assert np.mean(rel <= 1e-3) >= well.mean()
 
 
 # ---- host-buffer C ABI ---------------------------------------------------------------------------
@@ -497,14 +528,18 @@ def test_full_size_properties(engine):
     losses = a["losses"]
     assert torch.equal(a["best"].long(), torch.argmin(losses, dim=1))
     assert torch.isfinite(a["plan"]).all() and torch.isfinite(losses).all()
-    # spot-check 64 problems spread over the batch against the oracle
-    sel = np.linspace(0, B - 1, 64).astype(np.int64)
+    # spot-check 256 problems spread over the batch against the oracle: EVERY problem on which the reference itself is
+    # reproducible must match (winner and plan); a disagreement is only admissible where the oracle's own f32 / f64 /
+    # ulp-noise probes disagree, and those must stay a small minority
+    sel = np.linspace(0, B - 1, 256).astype(np.int64)
     op = O.OracleParams()
-    ref = O.generate_plan_batch(op, batch["world"][sel], batch["weights"][batch["weight_idx"][sel]])
-    got = a["plan"].cpu().numpy()[sel]
-    same = ref["best"] == a["best"].cpu().numpy()[sel]
-    assert same.mean() > 0.9
-    assert np.max(np.abs(got[same] - ref["plan"][same])) <= 1e-3
+    ref, ref64, cond_u, cond_l = solve_conditioning(op, batch["world"][sel], batch["weights"][batch["weight_idx"][sel]])
+    well = (cond_u < 1e-5) & (ref["best"] == ref64["best"]) & (cond_l.max(1) < 2e-6)
+    got, gbest = a["plan"].cpu().numpy()[sel], a["best"].cpu().numpy()[sel]
+    bad = (gbest != ref["best"]) | (np.abs(got - ref["plan"]).reshape(len(sel), -1).max(1) > 1e-3)
+    assert well.mean() >= 0.75, well.mean()
+    assert not np.any(bad & well), np.nonzero(bad & well)[0]
+    assert bad.mean() <= 1.0 - well.mean()
 
 
 def test_kernel_forms_agree(engine, monkeypatch):

@@ -252,3 +252,117 @@ def test_kernel_form_selection(monkeypatch):
     assert ocd.kernel_form(ocd.PlannerParams(H=15), 4096) == "latency"   # no time-parallel form above H = 8: falls back
     with pytest.raises(ValueError):
         ocd.kernel_form(ocd.PlannerParams(H=65), 10)
+
+
+# ---- CMA-ES: strategy parameters against the closed forms of Hansen's tutorial, trajectories against fixtures ---------
+# (N, lambda, mu, mu_eff, c_sigma, d_sigma, c_c, c_1, c_mu, chi_N) from "The CMA Evolution Strategy: A Tutorial"
+# (Hansen 2016), Table 1, evaluated independently of cmaes.py for the two weight dimensions of the scenarios
+HANSEN_TABLE1 = [
+    (6, 9, 4, 2.840610429717054, 0.34973966316715493, 1.349739663167155, 0.40864968827481546, 0.03563118207139872,
+     0.03568631199675212, 2.3506677359645445),
+    (7, 9, 4, 2.840610429717054, 0.3261732698019042, 1.3261732698019042, 0.3730062293365141, 0.027882099260254246,
+     0.028450351990791156, 2.553831379703503),
+]
+
+
+@pytest.mark.parametrize("N,lam,mu,mueff,cs,ds,cc,c1,cmu,chi", HANSEN_TABLE1)
+def test_cmaes_strategy_parameters_are_the_tutorial_defaults(N, lam, mu, mueff, cs, ds, cc, c1, cmu, chi):
+    es = cmaes.CMAES([0.0] * N, 0.05, seed=1)
+    assert (es.lam, es.mu) == (lam, mu)
+    np.testing.assert_allclose(es.weights, [0.493738377484, 0.281096832481, 0.156709502558, 0.068455287477], atol=1e-12)
+    got = (es.mueff, es.cs, es.damps, es.cc, es.c1, es.cmu, es.chiN)
+    np.testing.assert_allclose(got, (mueff, cs, ds, cc, c1, cmu, chi), rtol=1e-13)
+    assert es.weights.sum() == pytest.approx(1.0) and abs(es.c1 + es.cmu) < 1       # a convex covariance update
+
+
+def test_cmaes_trajectories_match_the_fixtures():
+    """Fixed-seed runs on sphere / rotated ellipsoid (tests/golden/make_cmaes_golden.py): sampling order, update and
+    step-size path are pinned against accidental change (regression fixtures of the restatement, not pycma output)."""
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import make_cmaes_golden as G
+    for tr in load_golden("cmaes_trajectories.json"):
+        es = cmaes.CMAES(list(np.linspace(-0.5, 0.5, tr["N"])), tr["sigma0"], seed=tr["seed"])
+        for row in tr["generations"]:
+            pop = es.ask()
+            np.testing.assert_allclose(pop[0], row["first_candidate"], rtol=1e-12, atol=1e-15)
+            fit = [G.OBJ[tr["objective"]](x) for x in pop]
+            es.tell(fit)
+            assert min(fit) == pytest.approx(row["best_f"], rel=1e-10)
+            assert es.sigma == pytest.approx(row["sigma"], rel=1e-10)
+            np.testing.assert_allclose(es.mean, row["mean"], rtol=1e-9, atol=1e-12)
+        assert tr["generations"][-1]["best_f"] < tr["generations"][0]["best_f"]
+
+
+def test_cmaes_lockstep_runs_equal_serial_runs():
+    """R independent runs advanced in lock step (one batched evaluation per generation for all of them) take exactly
+    the steps they take alone: same candidates, same stopping generation, same result -- bit for bit."""
+    def f(x):
+        return float(np.sum((np.asarray(x) - 0.3) ** 2 * np.arange(1, len(x) + 1)))
+    x0s = [[0.0] * 6, [0.1] * 6, [-0.2] * 6, [0.5] * 6]
+    opts = [dict(seed=5, maxiter=12), dict(seed=6, maxiter=7), dict(seed=7, maxfevals=40), dict(seed=5, maxiter=12)]
+    serial = [cmaes.fmin2(f, x0, 0.05, o) for x0, o in zip(x0s, opts)]
+    calls = []
+
+    def multi(pops):
+        calls.append([len(p) for p in pops])
+        return [np.array([f(x) for x in p]) for p in pops]
+
+    lock = cmaes.fmin2_lockstep(multi, x0s, 0.05, opts)
+    for (xs, es_s), (xl, es_l) in zip(serial, lock):
+        assert np.array_equal(xs, xl) and es_s.countiter == es_l.countiter and es_s.counteval == es_l.counteval
+        assert es_s.sigma == es_l.sigma and np.array_equal(es_s.mean, es_l.mean)
+    assert len(calls) == 12 and calls[0] == [9, 9, 9, 9] and calls[-1] == [9, 0, 0, 9]     # runs drop out as they stop
+
+
+def test_torch_autograd_restatement_agrees_with_the_c_oracle():
+    """Two independent derivations of the planner's gradient: the C oracle's closed-form adjoint and torch autograd
+    on an op-for-op restatement of mpc_reward (oracle/torch_serial.py, the `cpu_ref_serial` baseline).  Same plans."""
+    import oracle as O
+    from oracle import torch_serial as TS
+    b = synthetic.make_batch(3, seed=5)
+    w = b["weights"][b["weight_idx"]]
+    ref = O.generate_plan_batch(O.OracleParams(n_iter=12), b["world"], w)
+    prob = TS.Problem(n_iter=12)
+    for i in range(3):
+        plan, losses, best = prob.generate_plan(b["world"][i], w[i])
+        assert best == ref["best"][i]
+        np.testing.assert_allclose(plan, ref["plan"][i], atol=2e-6)
+        np.testing.assert_allclose(losses, ref["losses"][i], rtol=2e-6, atol=2e-6)
+    # the replanning shape: two lanes, two other cars with known controls, target speed 1.2
+    b = synthetic.make_batch(2, C=3, lane_x=(-0.05, 0.05), seed=8)
+    w = b["weights"][b["weight_idx"]]
+    oc = 0.3 * synthetic.make_other_controls(2, 3, 5)
+    op = O.OracleParams(C=3, lane_x=(-0.05, 0.05), num_lanes=2, other_mode=1, target_speed=1.2, n_iter=8)
+    ref = O.generate_plan_batch(op, b["world"], w, other_controls=oc)
+    prob = TS.Problem(lane_x=(-0.05, 0.05), num_lanes=2, target_speed=1.2, n_iter=8)
+    for i in range(2):
+        plan, losses, best = prob.generate_plan(b["world"][i], w[i], other_controls=oc[i])
+        assert best == ref["best"][i]
+        np.testing.assert_allclose(plan, ref["plan"][i], atol=2e-6)
+
+
+def test_bind_rank_cpus_partitions_the_affinity_mask():
+    import os
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no affinity support")
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        if len(before) >= 2:
+            n = parallel.bind_rank_cpus(1, 2)
+            mine = sorted(os.sched_getaffinity(0))
+            assert n == len(before) // 2 and mine == before[len(before) // 2:2 * (len(before) // 2)]
+        os.sched_setaffinity(0, before)
+        assert parallel.bind_rank_cpus(0, 1) == len(before) and sorted(os.sched_getaffinity(0)) == before
+        assert parallel.bind_rank_cpus(0, len(before) + 1) == len(before)          # more ranks than cores: left alone
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_reference_arm_never_maps_the_cuda_library():
+    """bench.py --impl reference times the CPU oracle only: the process must not even load libocd_b200.so."""
+    code = ("import sys; sys.argv=['bench.py']; sys.path.insert(0, %r); import bench; bench.cpu_arm(64, 1); "
+            "maps = open('/proc/self/maps').read(); print('MAPPED' if 'libocd_b200' in maps else 'CLEAN', "
+            "'ORACLE' if 'libocd_oracle' in maps else 'NOORACLE')" % str(ROOT))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.split()[-2:] == ["CLEAN", "ORACLE"], out.stdout
