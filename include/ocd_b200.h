@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define OCD_ABI_VERSION 2
+#define OCD_ABI_VERSION 3
 #define OCD_MAX_LANES   4
 #define OCD_MAX_OTHER   7     /* other cars per world (C <= 8)            */
 #define OCD_MAX_PLAN    16    /* FixedPlanCar plan length                 */
@@ -221,11 +221,13 @@ int ocd_solve_first_host(ocd_ctx *ctx, const ocd_params *p, const float *world,
                          float *first_control /*[2][B]*/, float *losses /*[S][B] or NULL*/,
                          int32_t *best /*[B] or NULL*/, int64_t B);
 
+/* final_world [C][4][B] or NULL.  Repeated calls with the same shapes and constants (a CMA-ES run makes one per
+ * generation) replay a CUDA graph of copy-in / kernel / copy-out captured on the first of them. */
 int ocd_episode_batch_host(ocd_ctx *ctx, const ocd_params *p, const ocd_scenario *sc,
                            const float *robot_init, const float *other_init,
                            const float *plan_weights, int64_t Bw, const int32_t *weight_idx,
                            const float *true_weights, const int32_t *unlucky_idx,
-                           int32_t t0, int32_t T, float *returns, int64_t B);
+                           int32_t t0, int32_t T, float *returns, float *final_world, int64_t B);
 
 /* FP32 FMA micro-benchmark used by bench.py to measure the roofline denominator in the same
  * job: runs `iters` dependent-free FMA rounds on every SM, returns achieved FLOP/s in *flops. */

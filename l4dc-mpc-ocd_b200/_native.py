@@ -15,7 +15,7 @@ _HERE = Path(__file__).resolve().parent
 # OCD_B200_LIB: a variant build of the same library (scripts/tuning/build_variants.sh) for A/B measurements
 LIB_PATH = Path(os.environ["OCD_B200_LIB"]).resolve() if os.environ.get("OCD_B200_LIB") else _HERE / "libocd_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LANES, MAX_OTHER, MAX_PLAN, MAX_H, MAX_STARTS = 4, 7, 16, 64, 6
 LBFGS_MAX_H = 16
 OK, EINVAL, EUNSUP, ECUDA, ENOMEM = 0, -1, -2, -3, -4
@@ -75,7 +75,7 @@ _PROTOTYPES = {
     "ocd_ctx_destroy": (None, [_P]),
     "ocd_solve_batch_host": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64]),
     "ocd_solve_first_host": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _I64]),
-    "ocd_episode_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _P, _I64]),
+    "ocd_episode_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _P, _P, _I64]),
     "ocd_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
 }
 EXPORTS = tuple(_PROTOTYPES)

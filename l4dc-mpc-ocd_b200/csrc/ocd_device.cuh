@@ -788,14 +788,14 @@ __device__ __forceinline__ float solve_start(const KParams &k, const GradW &w, c
 // register-resident kernels' own, statement for statement.
 // ---------------------------------------------------------------------------------------------
 #ifndef OCD_Q_SF
-#define OCD_Q_SF 0
+#define OCD_Q_SF 1
 #endif
 __host__ __device__ inline int q_stride(int H) { return H | 1; }     // float4 per thread row
 
 // OCD_Q_CS = 1 (tuning): the saved (cos, sin) of every step travel through shared memory too (one float2 per step,
 // rows of HT + 1 float2 behind the float4 rows), which leaves only v_t and the controls in registers.
 #ifndef OCD_Q_CS
-#define OCD_Q_CS 0
+#define OCD_Q_CS 1
 #endif
 __host__ __device__ inline int q2_stride(int H) { return (H + 1) | 1; }                 // float2 per thread row
 __host__ __device__ inline int q_thread_floats(int H) { return 4 * q_stride(H) + (OCD_Q_CS ? 2 * q2_stride(H) : 0); }
@@ -809,7 +809,7 @@ __device__ __forceinline__ void forward_sweep_q(const KParams &k, const GradW &w
     float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
 #pragma unroll
     for (int t = 0; t < HT; ++t) {
-        if (SF) {
+        if (SF && t % (OCD_Q_SF > 0 ? OCD_Q_SF : 1) == 0) {     // a fence every OCD_Q_SF steps: groups of that many steps interleave
             int one;
             asm volatile("mov.u32 %0, 1;" : "=r"(one));
             if (one == 0) continue;
@@ -968,6 +968,7 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
             KE[j] = __shfl_sync(OCD_FULL, ke, j, kTG);
         }
         float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
+        float ld_ = 0.0f, mv_t = 0.0f, mth_t = 0.0f;         // the three adjoint terms of this lane's own step
 #pragma unroll
         for (int jj = 0; jj < HT; ++jj) {
             const int j = HT - 1 - jj;
@@ -977,18 +978,19 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
             const float mv = fmaf(KE[j], ss[j + 1], lv);
             const float mth = fmaf(__fmul_rn(KE[j], sv[j + 1]), sc[j + 1], lth);
             const float ld = fmaf(sc[j], mx, ss[j] * my);
-            const float a = A[j], om = W[j];
-            const bool in_a = (a >= -8.0f) && (a <= 4.0f);
-            const bool in_w = fabsf(om) <= 4.0f;
             lv = fmaf(fmaf(c1, sv[j], 1.0f), mv, fmaf(c2, sv[j], k.dt) * ld);
             lth = fmaf(sd[j], fmaf(sc[j], my, -(ss[j] * mx)), mth);
             lx = mx;
             ly = my;
-            const float na = in_a ? fmaf(lra, ld, fmaf(lrv, mv, a)) : a;
-            const float nw = in_w ? fmaf(lrv, mth, om) : om;
-            ua = (j == tt) ? na : ua;
-            uw = (j == tt) ? nw : uw;
+            const bool mine = j == tt;
+            ld_ = mine ? ld : ld_; mv_t = mine ? mv : mv_t; mth_t = mine ? mth : mth_t;
         }
+        // every lane walks the whole adjoint chain, but updates only its own control (same formula, same operands as
+        // the single-thread kernels' update of step tt)
+        const bool in_a = (ua >= -8.0f) && (ua <= 4.0f);
+        const bool in_w = fabsf(uw) <= 4.0f;
+        ua = in_a ? fmaf(lra, ld_, fmaf(lrv, mv_t, ua)) : ua;
+        uw = in_w ? fmaf(lrv, mth_t, uw) : uw;
     }
 #pragma unroll
     for (int j = 0; j < HT; ++j) {

@@ -38,8 +38,15 @@ namespace ocd {
 // The medium-horizon kernels (HT = 9..24, "Q" kernels: controls and saved states in registers, the rest of the
 // reverse sweep's inputs through shared memory) run straight-line code in every form: OCD_Q_REGS registers
 // (wide and throughput form), 255 for the latency form.
-#ifndef OCD_Q_REGS
-#define OCD_Q_REGS 128
+#ifdef OCD_Q_REGS_ALL
+#define OCD_Q_REGS(NOT_) OCD_Q_REGS_ALL
+#else
+#define OCD_Q_REGS(NOT_) ((NOT_) <= 2 ? 104 : 128)
+#endif
+// World-tile staging of the solve kernels: 1-D TMA bulk copies (stock) or per-thread loads (-DOCD_LDG_STAGE), see
+// stage_world_tile below
+#if !defined(OCD_TMA_STAGE) && !defined(OCD_LDG_STAGE)
+#define OCD_TMA_STAGE 1
 #endif
 #define OCD_IS_Q(HT) ((HT) >= 9 && (HT) <= 24)
 // Long compile-time horizons (HT >= 25, FAST): the segmented adjoint with a constant segment count
@@ -50,9 +57,12 @@ namespace ocd {
 #ifndef OCD_SEGC_FR
 #define OCD_SEGC_FR 1
 #endif
+#ifndef OCD_SEGC_SEG
+#define OCD_SEGC_SEG 5      // steps per segment of the long compile-time horizons (checkpoint rows are sized for 5)
+#endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT) ? OCD_Q_REGS : OCD_IS_SEGC(HT) ? OCD_SEGC_REGS : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
+    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT) ? OCD_SEGC_REGS : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -116,9 +126,57 @@ struct Smem {
     float *useg;    // [S*P][2H | 1]     controls of every thread (segmented kernels only)
     float *ckpt;    // [S*P][4 nseg | 1] segment-start states (segmented kernels only)
     float4 *q;      // [S*P][H | 1]      (d_t, gx, hy, ke) of every step (medium-horizon Q kernels only; first in the carve-up)
+#ifdef OCD_TMA_STAGE
+    float *tile;    // [C*4][P]          world tile staged by bulk copies (A/B variant)
+#endif
 };
 
 static constexpr int kSeg = 5;    // steps per segment of the runtime-horizon kernels (register budget of the H=5 kernel)
+
+// ---------------------------------------------------------------------------------------------
+// OCD_TMA_STAGE (on in the stock build; -DOCD_LDG_STAGE builds the per-thread-LDG variant -- the A/B measurement is in
+// DESIGN.md and profiles/tuning/r02_tma_ab.log): stage the block's world
+// tile [C*4][P] with 1-D bulk copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx; SASS UBLKCP)
+// instead of per-thread LDG.  One elected thread arms the barrier with the tile's byte count and issues one copy
+// per row (P consecutive problems = P*4 bytes, 16-byte aligned when B % 4 == 0 and the block is full); every
+// thread then waits on the barrier's phase 0.  Ragged blocks and odd batch sizes take the plain loads.
+// ---------------------------------------------------------------------------------------------
+#ifdef OCD_TMA_STAGE
+template <int P>
+__device__ __forceinline__ void stage_world_tile(float *tile, const float *world, long long B, long long b0, int rows,
+                                                 bool live_all, unsigned long long *bar) {
+    const bool tma_ok = live_all && (B % 4 == 0) && (P % 4 == 0);
+    if (tma_ok) {
+        const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)(rows * P * sizeof(float));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+            for (int r = 0; r < rows; ++r) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + r * P);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(world + (size_t)r * B + b0), "r"((unsigned)(P * sizeof(float))), "r"(bar_s)
+                             : "memory");
+            }
+        }
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_s) : "memory");
+    } else {
+        for (int i = threadIdx.x; i < rows * P; i += blockDim.x) {
+            const int r = i / P, q = i % P;
+            const long long b = b0 + q < B ? b0 + q : B - 1;
+            tile[i] = world[(size_t)r * B + b];
+        }
+        __syncthreads();
+    }
+}
+#endif
 
 // lin: the slab holds (x0, dx, y0, dy) per other car instead of a position per horizon step
 // (worth its two extra FFMA per car and step only once the per-step slab would crowd out resident blocks)
@@ -132,6 +190,9 @@ __host__ __device__ inline size_t smem_floats(int H, int NO, int K, int S, int P
     if (episode) n += (size_t)S * 2 * P + (size_t)(NO + 1) * 4 * P + ((K + 3) / 4) * 4;
     if (seg) n += (size_t)S * P * (seg_u_stride(H) + seg_ck_stride(H, kSeg));
     if (qk) n += (size_t)S * P * q_thread_floats(H);
+#ifdef OCD_TMA_STAGE
+    if (!episode) n += (size_t)(NO + 1) * 4 * P + 4;      // the staged world tile (16-byte aligned) and its mbarrier
+#endif
     return n;
 }
 
@@ -140,6 +201,10 @@ __device__ __forceinline__ Smem carve(float *base, const KParams &k, int P, bool
     Smem m;
     m.q = reinterpret_cast<float4 *>(base);            // 16-byte aligned: the float4 rows come first
     if (qk) base += (size_t)k.S * P * q_thread_floats(k.H);
+#ifdef OCD_TMA_STAGE
+    m.tile = base;                                     // [C*4][P] world tile, then the mbarrier (solve kernels)
+    if (!episode) base += (size_t)(k.NO + 1) * 4 * P + 4;
+#endif
     m.oth = base;
     m.wraw = m.oth + (size_t)(lin ? 4 * k.NO : k.H * k.NO * 2) * P;
     m.loss = m.wraw + (size_t)k.K * P;
@@ -206,23 +271,32 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     const long long b = live ? b_raw : a.B - 1;
     const long long B = a.B;
 
+#ifdef OCD_TMA_STAGE
+    const float *wsrc = m.tile + p;                    // this problem's column of the staged tile
+    const long long wstr = P;
+    stage_world_tile<P>(m.tile, a.world, B, (long long)blockIdx.x * P, (k.NO + 1) * 4, (long long)blockIdx.x * P + P <= B,
+                        reinterpret_cast<unsigned long long *>(m.tile + (size_t)(k.NO + 1) * 4 * P));
+#else
+    const float *wsrc = a.world + b;
+    const long long wstr = B;
+#endif
     if (s == 0) {
         const long long wc = weight_column(a.weight_idx, a.Bw, b);
         for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.weights[(size_t)i * a.Bw + wc];
         for (int j = 0; j < k.NO; ++j) {
-            const float *st = a.world + (size_t)(j + 1) * 4 * B + b;
+            const float *st = wsrc + (size_t)(j + 1) * 4 * wstr;
             const float *oc = nullptr;
             long long ocs = 0;
             if (k.other_mode == 1) {
                 ocs = a.Bo;
                 oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
             }
-            predict_other<PRECISE>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P, lin);
+            predict_other<PRECISE>(k, st[0], st[wstr], st[2 * wstr], st[3 * wstr], oc, ocs, m.oth + p, j, P, lin);
         }
     }
     __syncthreads();
 
-    const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
+    const float x0 = wsrc[0], y0 = wsrc[wstr], v0 = wsrc[2 * wstr], th0 = wsrc[3 * wstr];
     const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     const float speed = a.cur_speed ? a.cur_speed[b] : v0;
     const int H = HT > 0 ? HT : k.H;
@@ -232,11 +306,12 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     if constexpr (SEGK) {
         constexpr int HC = HT;                       // 0: runtime horizon
         constexpr bool FR = HC > 0 && OCD_SEGC_FR && !PRECISE;
+        constexpr int SEGL = HC > 0 ? OCD_SEGC_SEG : kSeg;
         float *ck = m.ckpt + (size_t)threadIdx.x * seg_ck_stride(k.H, kSeg);
         loss = (!PRECISE && lin)
-                   ? solve_start_seg<kSeg, NOT_, LT, PRECISE, !PRECISE, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   ? solve_start_seg<SEGL, NOT_, LT, PRECISE, !PRECISE, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                                       m.oth + p, P, s, speed, us, ck)
-                   : solve_start_seg<kSeg, NOT_, LT, PRECISE, false, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
+                   : solve_start_seg<SEGL, NOT_, LT, PRECISE, false, LAT, HC, FR>(k, gw, m.wraw + p, P, x0, y0, v0, th0,
                                                                                   m.oth + p, P, s, speed, us, ck);
     } else if constexpr (QK) {
         init_start<HT>(k, s, speed, u);
@@ -434,22 +509,31 @@ __global__ void __launch_bounds__(6 * kTP * kTG, 1) k_solve_tp(const __grid_cons
     const bool live = b_raw < a.B;
     const long long b = live ? b_raw : a.B - 1;
     const long long B = a.B;
+#ifdef OCD_TMA_STAGE
+    const float *wsrc = m.tile + p;
+    const long long wstr = P;
+    stage_world_tile<P>(m.tile, a.world, B, (long long)blockIdx.x * P, (k.NO + 1) * 4, (long long)blockIdx.x * P + P <= B,
+                        reinterpret_cast<unsigned long long *>(m.tile + (size_t)(k.NO + 1) * 4 * P));
+#else
+    const float *wsrc = a.world + b;
+    const long long wstr = B;
+#endif
     if (s == 0 && t == 0) {
         const long long wc = weight_column(a.weight_idx, a.Bw, b);
         for (int i = 0; i < k.K; ++i) m.wraw[i * P + p] = a.weights[(size_t)i * a.Bw + wc];
         for (int j = 0; j < k.NO; ++j) {
-            const float *st = a.world + (size_t)(j + 1) * 4 * B + b;
+            const float *st = wsrc + (size_t)(j + 1) * 4 * wstr;
             const float *oc = nullptr;
             long long ocs = 0;
             if (k.other_mode == 1) {
                 ocs = a.Bo;
                 oc = a.other_controls + (size_t)j * k.H * 2 * a.Bo + (a.Bo == 1 ? 0 : b);
             }
-            predict_other<false>(k, st[0], st[B], st[2 * B], st[3 * B], oc, ocs, m.oth + p, j, P, false);
+            predict_other<false>(k, st[0], st[wstr], st[2 * wstr], st[3 * wstr], oc, ocs, m.oth + p, j, P, false);
         }
     }
     __syncthreads();
-    const float x0 = a.world[b], y0 = a.world[B + b], v0 = a.world[2 * B + b], th0 = a.world[3 * B + b];
+    const float x0 = wsrc[0], y0 = wsrc[wstr], v0 = wsrc[2 * wstr], th0 = wsrc[3 * wstr];
     const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     float a0, w0;
     tp_start_controls(k, s, a.cur_speed ? a.cur_speed[b] : v0, a0, w0);

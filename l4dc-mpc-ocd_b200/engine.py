@@ -346,7 +346,7 @@ class Engine:
             rc = N.lib.ocd_feature_jacobian_batch(C.addressof(ps), _ptr(ws), _ptr(us), _ptr(oc), Bo, _ptr(phi),
                                                   _ptr(jac), B, self._stream())
         N.check(rc, "ocd_feature_jacobian_batch")
-        self._kernel_launches += p.K if B else 0
+        self._kernel_launches += 1 if B else 0
         return phi.t().contiguous(), jac.permute(3, 0, 1, 2).contiguous()
 
     def features(self, p: PlannerParams, world) -> torch.Tensor:
@@ -522,8 +522,10 @@ class HostContext:
 
     def episodes_soa(self, p: PlannerParams, sc: Scenario, robot_init: np.ndarray, plan_weights: np.ndarray,
                      true_weights: np.ndarray, T: int, weight_idx=None, other_init=None, unlucky_idx=None,
-                     t0: int = 0) -> np.ndarray:
-        """Host SoA arrays: robot_init [4][B], plan_weights [K][Bw], true_weights [K] -> returns [B]."""
+                     t0: int = 0, final_world: bool = False, structs=None):
+        """Host SoA arrays: robot_init [4][B], plan_weights [K][Bw], true_weights [K] -> returns [B]
+        (with final_world=True: (returns, final world [C][4][B])).  `structs`: a cached (ocd_params, ocd_scenario) pair
+        for callers that make the same call over and over (MPC_ORD)."""
         ri = np.ascontiguousarray(robot_init, np.float32)
         w = np.ascontiguousarray(plan_weights, np.float32)
         tw = np.ascontiguousarray(true_weights, np.float32)
@@ -532,9 +534,10 @@ class HostContext:
         oi = None if other_init is None else np.ascontiguousarray(other_init, np.float32)
         ul = None if unlucky_idx is None else np.ascontiguousarray(unlucky_idx, np.int32)
         ret = np.empty((B,), np.float32)
-        ps, ss = p.c_struct(), sc.c_struct()
+        fw = np.empty((p.C, 4, B), np.float32) if final_world else None
+        ps, ss = structs if structs is not None else (p.c_struct(), sc.c_struct())
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         rc = N.lib.ocd_episode_batch_host(self._h, C.addressof(ps), C.addressof(ss), vp(ri), vp(oi), vp(w), Bw,
-                                          vp(idx), vp(tw), vp(ul), int(t0), int(T), vp(ret), B)
+                                          vp(idx), vp(tw), vp(ul), int(t0), int(T), vp(ret), vp(fw), B)
         N.check(rc, "ocd_episode_batch_host")
-        return ret
+        return (ret, fw) if final_world else ret

@@ -236,29 +236,27 @@ class MPC_ORD:
 
     # -- reference API -----------------------------------------------------------------------------------
     def _episode_returns_cached(self, eng, W, robot, widx, unlucky):
-        """-> (returns [B] host, final world [C, 4] of the last episode); see episode_returns."""
-        import torch
+        """-> (returns [B] host, final world [C, 4] of the last episode); see episode_returns.
+        The CMA-ES hot loop: numpy in, numpy out through `ocd_episode_batch_host`, whose context keeps the staging
+        buffers and replays ONE captured CUDA graph (copy-in, episode kernel, copy-out) per generation; the SoA
+        transposes of everything but the candidates and the two C structs are cached here."""
+        from ...runtime import get_host_context
         p, sc = self.program.params, self.program.scenario
-        B, dev = robot.shape[0], eng.device
-        key = (robot.tobytes(), widx.tobytes(), None if unlucky is None else unlucky.tobytes(), str(dev),
+        B = robot.shape[0]
+        key = (robot.tobytes(), widx.tobytes(), None if unlucky is None else unlucky.tobytes(),
                as_f32(self.designer_weights).tobytes())
         c = self._dev_cache.get(key)
         if c is None:
             if len(self._dev_cache) >= 8:
                 self._dev_cache.clear()
-            c = dict(ri=torch.as_tensor(np.ascontiguousarray(robot.T), device=dev),
-                     idx=torch.as_tensor(widx, device=dev),
-                     tw=torch.as_tensor(as_f32(self.designer_weights), device=dev),
-                     ul=None if unlucky is None else torch.as_tensor(unlucky, device=dev),
-                     out=torch.empty(((1 + p.C * 4) * B,), dtype=torch.float32, device=dev))
+            c = dict(ri=np.ascontiguousarray(robot.T), idx=np.ascontiguousarray(widx, np.int32),
+                     tw=as_f32(self.designer_weights), ul=None if unlucky is None else np.ascontiguousarray(unlucky, np.int32),
+                     structs=(p.c_struct(), sc.c_struct()))
             self._dev_cache[key] = c
-        w = torch.as_tensor(np.ascontiguousarray(W.T), device=dev)                   # [K][n_cand]
-        buf = c["out"]
-        views = dict(returns=buf[:B], final_world=buf[B:].view(p.C, 4, B))
-        eng.episodes_soa(p, sc, c["ri"], w, W.shape[0], c["tw"], self.designer_horizon, weight_idx=c["idx"],
-                         unlucky_idx=c["ul"], final_world=True, out=views)
-        host = buf.cpu().numpy()
-        return host[:B], host[B:].reshape(p.C, 4, B)[:, :, -1]
+        ret, fw = get_host_context(self._device).episodes_soa(
+            p, sc, c["ri"], np.ascontiguousarray(W.T), c["tw"], self.designer_horizon, weight_idx=c["idx"],
+            unlucky_idx=c["ul"], final_world=True, structs=c["structs"])
+        return ret, fw[:, :, -1]
 
     def eval_weights_for_init(self, init, weights, render=False, heatmap_show=False):
         """Return of `weights` from one initial state, summed over the samples (reference :67-106)."""

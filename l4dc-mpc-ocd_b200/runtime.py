@@ -6,9 +6,10 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .engine import Engine
+from .engine import Engine, HostContext
 
 _engines: Dict[int, Engine] = {}
+_host_contexts: Dict[int, HostContext] = {}
 _default_device: Optional[int] = None
 
 
@@ -28,6 +29,15 @@ def get_engine(device: Optional[int] = None) -> Engine:
     if device not in _engines:
         _engines[device] = Engine(device)
     return _engines[device]
+
+
+def get_host_context(device: Optional[int] = None) -> HostContext:
+    """The host-buffer context (`ocd_ctx`) of `device`: numpy in, numpy out, staging buffers and the captured
+    episode-call graph kept between calls."""
+    idx = get_engine(device).device.index or 0
+    if idx not in _host_contexts:
+        _host_contexts[idx] = HostContext(idx)
+    return _host_contexts[idx]
 
 
 def as_f32(x, shape=None) -> np.ndarray:

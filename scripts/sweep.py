@@ -17,7 +17,7 @@ sys.path.insert(0, str(ROOT))
 import l4dc_mpc_ocd_b200 as ocd                  # noqa: E402
 from l4dc_mpc_ocd_b200 import synthetic         # noqa: E402
 
-LR = {5: 0.1, 15: 0.03, 50: 0.003}               # the reference's lr=0.1 is only stable at its own H=5/6
+LR = {5: 0.1, 15: 0.02, 50: 0.0003}              # the reference's lr=0.1 is only stable at its own H=5/6 (bench.py: SWEEP_LR)
 
 
 def main():
@@ -25,8 +25,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--horizons", type=int, nargs="*", default=[5, 15, 50])
-    ap.add_argument("--cars", type=int, nargs="*", default=[2, 4, 6])
-    ap.add_argument("--sizes", type=int, nargs="*", default=[4096, 65536, 1048576])
+    ap.add_argument("--cars", type=int, nargs="*", default=[2, 3, 4, 5, 6])
+    ap.add_argument("--sizes", type=int, nargs="*", default=[4096, 16384, 65536, 262144, 1048576])
     args = ap.parse_args()
     eng = ocd.Engine(0)
     peak = eng.fp32_peak(8192)
@@ -35,8 +35,6 @@ def main():
         for C in args.cars:
             for B in args.sizes:
                 if args.quick and B > 65536:
-                    continue
-                if H * B > 50 * 262144 * 2:          # keep the slowest points to a few seconds
                     continue
                 p = ocd.PlannerParams(H=H, C=C, lr=LR.get(H, 0.1))
                 b = synthetic.make_batch(B, C=C, seed=99)
@@ -55,9 +53,10 @@ def main():
                 ms = e0.elapsed_time(e1) / reps
                 fl = synthetic.flops_per_solve(H, C, 3)
                 finite = bool(torch.isfinite(out["losses"]).all().item())
-                row = dict(H=H, C=C, B=B, lr=p.lr, ms=ms, solves_per_s=B / (ms * 1e-3),
+                nominal = 148 * 128 * 2 * 1.965e9
+                row = dict(H=H, C=C, B=B, lr=p.lr, ms=ms, solves_per_s=B / (ms * 1e-3), form=ocd.kernel_form(p, B),
                            tflops=fl * B / (ms * 1e-3) / 1e12, frac_of_measured_fp32=fl * B / (ms * 1e-3) / peak,
-                           all_losses_finite=finite)
+                           frac_of_nominal_fp32=fl * B / (ms * 1e-3) / nominal, all_losses_finite=finite)
                 rows.append(row)
                 print(json.dumps(row), flush=True)
     if args.out:

@@ -7,9 +7,13 @@ set -eu
 NAME=$1; UNIT=$2; FLAGS=$3
 ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 CS=$ROOT/l4dc-mpc-ocd_b200/csrc
-OUT=$ROOT/scratch/var_$NAME
+OUT=$ROOT/scratch/var/$NAME
 mkdir -p "$OUT"
-NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I$ROOT/include -I$CS -Xptxas -v"
+# objects without -lineinfo (a quarter of the size: the variant libraries must fit gpurun's snapshot limit)
+NL=$ROOT/scratch/var/build_nl
+[ -d "$NL" ] && [ "$NL" -nt "$CS/ocd_device.cuh" ] && [ "$NL" -nt "$CS/ocd_kernels.cuh" ] && [ "$NL" -nt "$CS/ocd_api.cu" ] || {
+  rm -rf "$NL"; make -s -j8 -C "$CS" BUILD="$NL" OUT="$ROOT/scratch/var/libocd_nl.so" LINEINFO= >/dev/null; touch "$NL"; }
+NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -I$ROOT/include -I$CS -Xptxas -v"
 case $UNIT in
   solve_*) IFS=_ read -r _ HT NO LT <<< "$UNIT"
            $NV $FLAGS -DOCD_SOLVE_ONLY -DOCD_PRECISE=0 -DOCD_HT=$HT -DOCD_NO=$NO -DOCD_LT=$LT -c $CS/ocd_inst.cu -o $OUT/$UNIT.o 2> $OUT/ptxas.log ;;
@@ -17,6 +21,6 @@ case $UNIT in
            $NV $FLAGS -DOCD_PRECISE=$PR -DOCD_HT=$HT -DOCD_NO=$NO -DOCD_LT=$LT -c $CS/ocd_inst.cu -o $OUT/$UNIT.o 2> $OUT/ptxas.log ;;
   api)     $NV $FLAGS -c $CS/ocd_api.cu -o $OUT/api.o 2> $OUT/ptxas.log ;;
 esac
-OBJS=$(ls $CS/build/*.o | grep -v "/$UNIT.o")
+OBJS=$(ls $NL/*.o | grep -v "/$UNIT.o")
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/scratch/libocd_$NAME.so $OBJS $OUT/$UNIT.o
 grep -E "spill|registers" $OUT/ptxas.log | paste - - | sed 's/ptxas info    ://g' | head -6

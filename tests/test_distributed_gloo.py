@@ -51,3 +51,59 @@ def test_two_rank_sharded_returns(tmp_path):
         got = np.load(tmp_path / f"r{r}.npy")
         assert got.shape == (B,)
         np.testing.assert_array_equal(got, ref)
+
+
+class _OracleEngine:
+    """Stands in for the GPU engine on CPU ranks: the oracle evaluates the episodes; the final world of episode b is
+    tagged with b so that the test can see which episode's state each rank is left with."""
+
+    def __init__(self, O, spec, offset):
+        self.O, self.spec, self.offset = O, spec, offset
+
+    def episodes(self, p, sc, robot_init, plan_weights, true_weights, T, weight_idx=None, unlucky_idx=None,
+                 final_world=False, **_):
+        ri = np.asarray(robot_init, np.float32)
+        W = np.asarray(plan_weights, np.float32)[np.asarray(weight_idx)]
+        ret = self.O.episode_batch(self.spec.params, self.spec.scenario, ri, W, np.asarray(true_weights, np.float32), T,
+                                   nthreads=1)
+        fw = np.zeros((ri.shape[0], p.C, 4), np.float32)
+        fw[:, 0, :] = ri                     # tag: the episode's own initial state
+        return dict(returns=torch.from_numpy(ret), final_world=torch.from_numpy(fw))
+
+
+def _lockstep_worker(rank, ws, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    import pickle
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import oracle as O
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import mpc_ord as M
+    spec = O.scenario_params("finite_horizon")
+    M.get_engine = lambda device=None: _OracleEngine(O, spec, 0)
+    _, _, inits = M.finite_horizon_env(env_seeds=[1000000 + i for i in range(5)], debug=False)
+    runs = []
+    for g in (inits[0:2], inits[2:3], inits[3:5]):
+        car, world, _ = M.finite_horizon_env(debug=False)
+        runs.append(M.MPC_ORD(world, car, g, 3, verbose=False))
+    M.optimize_cmaes_lockstep(runs, [5, 6, 7], sigma0=0.05, maxfevals=18)
+    state = [([(w.tolist(), float(v)) for w, v in r.history], np.asarray(r.world.cars[0].state).tolist()) for r in runs]
+    with open(os.path.join(out_dir, f"lock{rank}.pkl"), "wb") as f:
+        pickle.dump(state, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_lockstep_cmaes_is_rank_consistent(tmp_path):
+    """Three independent CMA-ES runs in lock step over two ranks: the episodes of every generation are sharded, returns
+    AND final worlds all-gathered, so both ranks hold the same histories and leave the same state in the Python
+    objects (the state of each run's LAST episode, wherever it was computed)."""
+    import pickle
+    ws = 2
+    mp.spawn(_lockstep_worker, args=(ws, _free_port(), str(tmp_path)), nprocs=ws, join=True)
+    a = pickle.load(open(tmp_path / "lock0.pkl", "rb"))
+    b = pickle.load(open(tmp_path / "lock1.pkl", "rb"))
+    assert a == b
+    assert [len(h) for h, _ in a] == [19, 19, 19]
+    for (hist, state), n_inits in zip(a, (2, 1, 2)):
+        assert all(np.isfinite(v) for _, v in hist)

@@ -47,12 +47,22 @@ def test_two_iterations_every_problem_every_start(engine, mode, _n, H, C, lanes,
     # two updates of size lr * gradient: the controls carry the gradient's error scaled by lr
     tol_u = (2e-5 if mode == ocd.MATH_PRECISE else 2e-4) * max(1.0, lr / 0.1)
     assert np.max(np.abs(res["all_plans"] - ref["all_plans"])) <= tol_u
+    # the loss the engine reports for ITS controls is the objective of those controls (f64 oracle at the engine's
+    # controls: a difference in the controls, allowed above, times a large gradient is not a loss error)
+    w64 = w_full.astype(np.float64)
+    for s_ in range(op.S):
+        R = np.array([O.mpc_reward(op, batch["world"][b].astype(np.float64), res["all_plans"][b, s_].astype(np.float64), w64[b],
+                                   other_controls=None if oc is None else oc[b].astype(np.float64), dtype=np.float64,
+                                   grad=False) for b in range(0, B, 4)])
+        got = res["losses"][::4, s_]
+        assert np.max(np.abs(got + R) / np.maximum(1.0, np.abs(R))) <= OBJ_TOL[mode]
+    # and it is close to the oracle's own loss: within the objective tolerance plus what the control tolerance can move it
     rel = np.abs(res["losses"] - ref["losses"]) / np.maximum(1.0, np.abs(ref["losses"]))
-    assert rel.max() <= OBJ_TOL[mode] * (1 if H <= 15 else 3)
-    # winners: identical wherever the oracle's two best losses are further apart than the loss tolerance
+    assert rel.max() <= OBJ_TOL[mode] + 50.0 * tol_u
+    # winners: identical wherever the oracle's two best losses are further apart than that
     srt = np.sort(ref["losses"], axis=1)
-    clear = (srt[:, 1] - srt[:, 0]) > 4 * OBJ_TOL[mode] * np.maximum(1.0, np.abs(srt[:, 0]))
-    assert clear.mean() > 0.9
+    clear = (srt[:, 1] - srt[:, 0]) > 4 * (OBJ_TOL[mode] + 50.0 * tol_u) * np.maximum(1.0, np.abs(srt[:, 0]))
+    assert clear.mean() > 0.8
     assert np.array_equal(res["best"][clear], ref["best"][clear])
 
 

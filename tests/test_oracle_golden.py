@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle as O
+from l4dc_mpc_ocd_b200 import synthetic
 from conftest import load_golden
 
 F32 = np.float32
@@ -207,3 +208,85 @@ def test_golden_files_regenerate_from_the_reference(part, tmp_path):
     for d in (new, old):
         d.pop("generator_seconds", None)
     assert new == old
+
+
+# ---- the opt-in L-BFGS: ring-buffer semantics (a rejected pair must not overwrite a live one) -----------------------
+M, LS = 4, 6
+def lbfgs_py(op, world, w, u0, buggy=False, log=None):
+    """float64 restatement of the engine's L-BFGS for ONE start (oracle/ocd_oracle_impl.inc ocdo_lbfgs_start)."""
+    n = 2 * op.H
+    def fg(u, grad=True):
+        r = O.mpc_reward(op, world, u.reshape(op.H, 2), w, dtype=np.float64, grad=grad)
+        return (-r[0], -r[1].reshape(-1)) if grad else -r
+    u = u0.copy(); f, g = fg(u)
+    S = np.zeros((M, n)); Y = np.zeros((M, n)); rho = np.zeros(M)
+    k = head = 0; sy_last, yy_last = 0.0, 1.0
+    for it in range(op.n_iter):
+        q = g.copy(); al = np.zeros(M)
+        for i in range(k):
+            idx = (head - 1 - i + 2 * M) % M
+            dot = 0.0
+            for j in range(n): dot += S[idx][j] * q[j]
+            al[i] = rho[idx] * dot
+            q -= al[i] * Y[idx]
+        gamma = sy_last / yy_last if k > 0 else op.lr
+        q = gamma * q
+        for i in range(k - 1, -1, -1):
+            idx = (head - 1 - i + 2 * M) % M
+            dot = 0.0
+            for j in range(n): dot += Y[idx][j] * q[j]
+            b = rho[idx] * dot
+            q += S[idx] * (al[i] - b)
+        d = -q; gd = 0.0
+        for j in range(n): gd += g[j] * d[j]
+        if not (gd < 0):
+            k = 0; d = -op.lr * g; gd = 0.0
+            for j in range(n): gd += g[j] * d[j]
+        if not (gd < 0): break
+        t = 1.0; ok = False
+        for ls in range(LS):
+            ut = u + t * d
+            ft = fg(ut, False)
+            if ft <= f + (1e-4 * t) * gd: ok = True; break
+            t *= 0.5
+        if not ok: break
+        ft2, gt = fg(ut)
+        sj = ut - u; yj = gt - g
+        if buggy:
+            S[head] = sj; Y[head] = yj
+        sy = 0.0; yy = 0.0
+        for j in range(n): sy += sj[j] * yj[j]; yy += yj[j] * yj[j]
+        if yy > 0 and sy > 1e-10 * yy:
+            S[head] = sj; Y[head] = yj
+            rho[head] = 1.0 / sy; head = (head + 1) % M
+            if k < M: k += 1
+            sy_last, yy_last = sy, yy
+        elif log is not None:
+            log.append((it, k))
+        u, g, f = ut, gt, ft
+    return u
+
+
+
+def test_lbfgs_rejected_pair_keeps_the_live_pairs():
+    """With an Armijo-only line search on a non-convex objective the curvature test s.y > 1e-10 y.y fails now and then.
+    Once the ring of 4 pairs is full, slot `head` holds the OLDEST LIVE pair; a rejected candidate must leave it alone
+    (round 1 wrote the candidate there first: later directions were built on a corrupted pair).  A statement-for-
+    statement Python restatement of the algorithm locates starts where a rejection follows a full ring, and the C twin
+    of the kernel must take exactly the fixed path there -- which differs grossly from the overwriting one."""
+    op = O.OracleParams(H=5, C=2, n_iter=30, optimizer=1)
+    b = synthetic.make_batch(400, seed=3)
+    starts = ((0.0, 0.0), (0.0, -0.65), (0.0, 0.65))
+    hit = 0
+    for i, s in ((1, 2), (7, 2), (8, 1)):
+        w = b["weights"][b["weight_idx"][i]].astype(np.float64)
+        world = b["world"][i].astype(np.float64)
+        u0 = np.tile(starts[s], op.H).astype(np.float64)
+        log = []
+        fixed = lbfgs_py(op, world, w, u0, log=log)
+        assert any(k == M for _, k in log), "expected a rejected pair after the ring filled up"
+        wrong = lbfgs_py(op, world, w, u0, buggy=True)
+        got = O.generate_plan(op, world, w, dtype=np.float64, all_plans=True)["all_plans"][s].reshape(-1)
+        np.testing.assert_allclose(got, fixed, rtol=0, atol=1e-9)
+        hit += int(np.abs(fixed - wrong).max() > 1e-3)
+    assert hit == 3
