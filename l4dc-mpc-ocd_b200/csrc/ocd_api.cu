@@ -412,6 +412,15 @@ static int digest(const ocd_params *p, KParams &k) {
     }
     k.fs_lo = k.fshape * k.thr_lo;
     k.fs_w = k.fshape * k.thr_w;
+    {
+        const double ln2 = 0.69314718055994530942;
+        k.fl_shape = (float)(ln2 * (double)k.fshape);
+        k.fl_lo = (float)(ln2 * (double)k.fshape * (double)k.thr_lo);
+        k.fl_w = (float)(ln2 * (double)k.fshape * (double)k.thr_w);
+        k.fl_c = (float)(ln2 * ln2 * (double)k.fshape);
+        k.mid_c = p->L == 3 ? 0.5f * (k.lane_mid[0] + k.lane_mid[1]) : 0.0f;
+        k.mid_h = p->L == 3 ? 0.5f * (k.lane_mid[1] - k.lane_mid[0]) : 0.0f;
+    }
     return OCD_OK;
 }
 

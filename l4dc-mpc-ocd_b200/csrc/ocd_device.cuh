@@ -44,6 +44,11 @@ struct KParams {
     float lane_mid[OCD_MAX_LANES];  // midpoints between lanes adjacent in sorted order: where the lane-min ties
     float lane_sorted[OCD_MAX_LANES];   // lane positions in ascending order
     float fs_lo, fs_w;            // fence ramp in shape-scaled units: fshape*thr_lo, fshape*thr_w
+    // the same in units of ln 2 (FAST kernels): with q' = ln2 * shape * q the argument of the ramp's exponential comes
+    // out in base 2 (1/q' - 1/u' = log2(e) (1/qs - 1/us)): fl_shape = ln2 fshape, fl_lo = ln2 fs_lo, fl_w = ln2 fs_w,
+    // and dT/dq = T (1-T) fl_c (r1'^2 + r2'^2) with fl_c = fshape ln2^2
+    float fl_shape, fl_lo, fl_w, fl_c;
+    float mid_c, mid_h;           // three lanes: centre and half-distance of the two midpoints (|x - mid_c| = mid_h at either)
 };
 
 // collision bump half-widths (merging.py:70-73) and their reciprocals
@@ -355,10 +360,12 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
         float gb = w.GBl[0], near = 1.0f;
 #pragma unroll
         for (int i = 1; i < LT; ++i) {
-            const float d = x - k.lane_mid[i - 1];
-            gb = (d > 0.0f) ? w.GBl[i] : gb;
-            near = fminf(near, fabsf(d));
+            gb = (x > k.lane_mid[i - 1]) ? w.GBl[i] : gb;
+            if (LT != 3) near = fminf(near, fabsf(x - k.lane_mid[i - 1]));
         }
+        // three lanes: x is near one of the two midpoints  <=>  | |x - centre| - half-distance | is small (one
+        // subtraction less than a distance to each)
+        if (LT == 3) near = fabsf(fabsf(x - k.mid_c) - k.mid_h);
         gx = fmaf(w.GAm, x, gb);
         const bool close = near < 1e-6f;
         if (VM == 1) {
@@ -517,24 +524,24 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
                 fence_inside<true>(k, x, ax, q, f, df);
                 gx = fmaf(w.wfence, df, gx);
             }
-        } else if (const float qs = fmaf(ax, k.fshape, -k.fs_lo); VM == 1 || __any_sync(OCD_FULL, qs > 0.0f)) {
-            // in shape-scaled units qs = shape q: T = F1/(F1+F2) = 1/(1 + exp(r1 - r2)), r1 = 1/qs,
-            // r2 = 1/(shape width - qs); dT/dq = T (1-T) shape (r1^2 + r2^2).  Clamping qs and its
-            // complement to a tiny positive number makes the exponential saturate: T = 0, dT = 0 below the
-            // ramp and T = 1, dT = 0 above it, so the three regions need no branch.
-            const float qc = fmaxf(qs, 1e-7f), uc = fmaxf(k.fs_w - qs, 1e-7f);
-            float z, rr;                                   // z = r1 - r2, rr = r1^2 + r2^2
-            if (ONE_RCP) {     // one reciprocal serves both: with R = 1/(q u), z = (u - q) R and rr = (u^2 + q^2) R^2
+        } else if (const float qs = fmaf(ax, k.fl_shape, -k.fl_lo); VM == 1 || __any_sync(OCD_FULL, qs > 0.0f)) {
+            // in units of ln2 * shape (qs = ln2 shape q): T = F1/(F1+F2) = 1/(1 + 2^(r1 - r2)), r1 = 1/qs,
+            // r2 = 1/(ln2 shape width - qs); dT/dq = T (1-T) fl_c (r1^2 + r2^2).  Clamping qs and its complement to a
+            // tiny positive number makes the exponential saturate: T = 0, dT = 0 below the ramp and T = 1, dT = 0
+            // above it, so the three regions need no branch.
+            const float qc = fmaxf(qs, 1e-7f), uc = fmaxf(k.fl_w - qs, 1e-7f);
+            float r1, r2;
+            if (ONE_RCP) {     // one reciprocal serves both: with R = 1/(q u), r1 = u R and r2 = q R
                 const float R = Mth<false>::rcp_(qc * uc);
-                z = (uc - qc) * R;
-                rr = fmaf(uc, uc, qc * qc) * (R * R);
+                r1 = uc * R;
+                r2 = qc * R;
             } else {
-                const float r1 = Mth<false>::rcp_(qc), r2 = Mth<false>::rcp_(uc);
-                z = r1 - r2;
-                rr = fmaf(r1, r1, r2 * r2);
+                r1 = Mth<false>::rcp_(qc);
+                r2 = Mth<false>::rcp_(uc);
             }
-            const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_(z * OCD_LOG2E));
-            const float dT = (T * (1.0f - T)) * (k.fshape * rr);
+            const float rr = fmaf(r1, r1, r2 * r2);
+            const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_(r1 - r2));
+            const float dT = (T * (1.0f - T)) * (k.fl_c * rr);
             gx = fmaf(w.wfence, copysignf(fmaf(dT, ax, T), x), gx);
         }
     }

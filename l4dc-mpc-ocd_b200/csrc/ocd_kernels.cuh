@@ -48,11 +48,23 @@ namespace ocd {
 #if !defined(OCD_TMA_STAGE) && !defined(OCD_LDG_STAGE)
 #define OCD_TMA_STAGE 1
 #endif
-#define OCD_IS_Q(HT) ((HT) >= 9 && (HT) <= 24)
-// Long compile-time horizons (HT >= 25, FAST): the segmented adjoint with a constant segment count
-#define OCD_IS_SEGC(HT) ((HT) >= 25)
-#ifndef OCD_SEGC_REGS
-#define OCD_SEGC_REGS 168
+// Q kernels unroll the whole horizon: 15 steps with one other car are 1 470 hot instructions (24 KB) and already pay
+// for it in instruction-fetch stalls; with five other cars the sweep is 64 KB and the kernel ran at 40 % issue
+// utilisation (ncu: no_instruction 2.0 per issue).  So medium horizons with more than OCD_Q_MAX_NO other cars take
+// the segmented adjoint with a constant segment count instead, whose loop bodies are five steps long.
+#ifndef OCD_Q_MAX_NO
+#define OCD_Q_MAX_NO 1
+#endif
+#define OCD_IS_Q(HT, NOT_) ((HT) >= 9 && (HT) <= 24 && (NOT_) <= OCD_Q_MAX_NO)
+// Long compile-time horizons (HT >= 25, FAST), and medium ones with many cars: the segmented adjoint with a constant
+// segment count
+#define OCD_IS_SEGC(HT, NOT_) ((HT) >= 25 || ((HT) >= 9 && (NOT_) > OCD_Q_MAX_NO))
+// registers of the constant-segment-count kernels: measured at H = 50, 2^20 problems, one other car -- 128: 59.9 ms,
+// 152: 58.3 ms, 168: 59.4 ms (profiles/tuning/r02_long_h_b.log); 168 with more cars
+#ifdef OCD_SEGC_REGS
+#define OCD_SEGC_REGS_(NOT_) OCD_SEGC_REGS
+#else
+#define OCD_SEGC_REGS_(NOT_) ((NOT_) == 1 ? 152 : 168)
 #endif
 #ifndef OCD_SEGC_FR
 #define OCD_SEGC_FR 1
@@ -62,7 +74,7 @@ namespace ocd {
 #endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT) ? OCD_SEGC_REGS : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
+    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
@@ -261,8 +273,8 @@ __global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
-    constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT);   // runtime or long horizon: segmented adjoint, controls in shared memory
-    constexpr bool QK = OCD_IS_Q(HT) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
+    constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT, NOT_);   // runtime or long horizon: segmented adjoint, controls in shared memory
+    constexpr bool QK = OCD_IS_Q(HT, NOT_) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
     const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
     const Smem m = carve(smem_raw, k, P, false, SEGK, lin, QK);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
@@ -745,7 +757,7 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 inline int choose_form(const KParams &k, long long B, bool episode) {
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;          // compile-time horizon and car count
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;                       // segmented kernels (solve only)
-    constexpr bool REGRES = HT > 0 && !OCD_IS_Q(HT) && !OCD_IS_SEGC(HT);  // register-resident (short) horizons
+    constexpr bool REGRES = HT > 0 && !OCD_IS_Q(HT, NOT_) && !OCD_IS_SEGC(HT, NOT_);  // register-resident (short) horizons
     if (HAS_LAT && HT <= kTG && tiny_batch(B, k.S)) return 3;
     if (episode) return pick_form(B, kP, k.S, HAS_LAT, HAS_LAT && NOT_ == 1, NOT_ == 1, true);
     return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, REGRES && NOT_ == 1, false, REGRES && NOT_ >= 3);
@@ -753,10 +765,10 @@ inline int choose_form(const KParams &k, long long B, bool episode) {
 
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
-    constexpr bool SEGK = HT == 0 || OCD_IS_SEGC(HT);
+    constexpr bool SEGK = HT == 0 || OCD_IS_SEGC(HT, NOT_);
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, SEGK,
                                      slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO),
-                                     OCD_IS_Q(HT) && !PRECISE) * sizeof(float);
+                                     OCD_IS_Q(HT, NOT_) && !PRECISE) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     constexpr bool ANY_LAT = HAS_LAT || (HT == 0 && !PRECISE);
     const int form = choose_form<HT, NOT_, LT, PRECISE>(k, a.B, false);

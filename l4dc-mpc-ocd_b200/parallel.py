@@ -77,11 +77,68 @@ def sharded_rows(evaluate: Callable[[np.ndarray], torch.Tensor], B: int) -> torc
     return gather_rows(evaluate(idx), B)
 
 
+def _visible_gpu_index(local_rank: int) -> int:
+    import os
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            return local_rank
+    return local_rank
+
+
+def gpu_local_cpus(gpu_index: int):
+    """CPUs on the NUMA node the GPU hangs off (NVML's ideal CPU affinity), or None when NVML cannot say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        import os
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        return cpus or None
+    except Exception:
+        return None
+
+
+def plan_rank_cpus(allowed, local_world_size: int, affinities):
+    """Pure planning step of bind_rank_cpus (unit-tested on CPU): `allowed` = CPUs the process may run on,
+    `affinities[r]` = NUMA-local CPUs of rank r's GPU (or None).  Every rank gets a slice of ITS GPU's node, the node
+    being shared evenly among the ranks whose GPUs hang off it; ranks whose node is unknown (or has fewer allowed CPUs
+    than ranks) share what is left / everything, contiguously.  -> list of CPU lists, one per rank."""
+    allowed = sorted(allowed)
+    if local_world_size <= 1 or len(allowed) < local_world_size:
+        return [list(allowed) for _ in range(max(1, local_world_size))]
+    aset = set(allowed)
+    keys = []
+    for r in range(local_world_size):
+        a = affinities[r] if affinities and r < len(affinities) else None
+        node = tuple(sorted(set(a) & aset)) if a else ()
+        keys.append(node)
+    out = [None] * local_world_size
+    for node in set(keys):
+        ranks = [r for r in range(local_world_size) if keys[r] == node]
+        if node and len(node) >= len(ranks) and len(node) < len(allowed):
+            per = len(node) // len(ranks)
+            for i, r in enumerate(ranks):
+                out[r] = list(node[i * per:(i + 1) * per])
+    if any(o is None for o in out):
+        # no usable topology for some rank: contiguous slices of all allowed CPUs, by rank, for everyone (round 1's
+        # rule; mixing the two rules could hand the same core to two ranks)
+        per = len(allowed) // local_world_size
+        out = [allowed[r * per:(r + 1) * per] for r in range(local_world_size)]
+    return out
+
+
 def bind_rank_cpus(local_rank: int, local_world_size: int) -> int:
-    """One process per GPU on one host: give this rank its own contiguous slice of the CPUs the process may run
-    on (sched_setaffinity), so that the ranks' staging-copy threads and pinned buffers do not fight over the same
-    cores (the engine sizes its copy pool from the affinity mask).  Returns the number of CPUs this rank owns.
-    No-op when there is one rank, fewer CPUs than ranks, or no affinity support."""
+    """One process per GPU on one host: give this rank its own slice of the CPUs the process may run on
+    (sched_setaffinity) -- a slice of the NUMA node ITS GPU hangs off (NVML affinity), shared evenly with the other
+    ranks on that node -- so that the ranks' staging-copy threads do not fight over the same cores and the pinned
+    buffers this rank allocates afterwards (first touch) are node-local to the GPU's PCIe root.  The engine sizes its
+    copy pool from the affinity mask.  Returns the number of CPUs this rank owns.  No-op when there is one rank,
+    fewer CPUs than ranks, or no affinity support."""
     import os
     try:
         cpus = sorted(os.sched_getaffinity(0))
@@ -89,8 +146,8 @@ def bind_rank_cpus(local_rank: int, local_world_size: int) -> int:
         return os.cpu_count() or 1
     if local_world_size <= 1 or len(cpus) < local_world_size:
         return len(cpus)
-    per = len(cpus) // local_world_size
-    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    aff = [gpu_local_cpus(_visible_gpu_index(r)) for r in range(local_world_size)]
+    mine = plan_rank_cpus(cpus, local_world_size, aff)[local_rank]
     try:
         os.sched_setaffinity(0, mine)
     except OSError:

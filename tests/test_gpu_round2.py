@@ -62,7 +62,7 @@ def test_two_iterations_every_problem_every_start(engine, mode, _n, H, C, lanes,
     # winners: identical wherever the oracle's two best losses are further apart than that
     srt = np.sort(ref["losses"], axis=1)
     clear = (srt[:, 1] - srt[:, 0]) > 4 * (OBJ_TOL[mode] + 50.0 * tol_u) * np.maximum(1.0, np.abs(srt[:, 0]))
-    assert clear.mean() > 0.8
+    assert clear.mean() > 0.25           # non-vacuity only: after two iterations many starts (extra_inits: pairs of them) are still near ties
     assert np.array_equal(res["best"][clear], ref["best"][clear])
 
 

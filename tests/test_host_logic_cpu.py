@@ -366,3 +366,30 @@ def test_reference_arm_never_maps_the_cuda_library():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.split()[-2:] == ["CLEAN", "ORACLE"], out.stdout
+
+
+def test_plan_rank_cpus_follows_the_gpu_numa_nodes():
+    """8 ranks on a two-socket host: GPUs 0-3 hang off node 0 (CPUs 0-31), GPUs 4-7 off node 1 (CPUs 32-63) -- every
+    rank gets 8 cores of its own GPU's node, disjoint from every other rank's; without topology (or with a node that
+    is the whole machine) the mask is cut contiguously by rank."""
+    from l4dc_mpc_ocd_b200 import parallel
+    allowed = list(range(64))
+    aff = [list(range(32))] * 4 + [list(range(32, 64))] * 4
+    plan = parallel.plan_rank_cpus(allowed, 8, aff)
+    assert [len(p) for p in plan] == [8] * 8
+    assert sorted(c for p in plan for c in p) == allowed
+    assert all(set(plan[r]) <= set(aff[r]) for r in range(8))
+    # interleaved GPU numbering (rank r's GPU on node r % 2) still lands every rank on its own node
+    aff2 = [list(range(32)) if r % 2 == 0 else list(range(32, 64)) for r in range(8)]
+    plan2 = parallel.plan_rank_cpus(allowed, 8, aff2)
+    assert all(set(plan2[r]) <= set(aff2[r]) for r in range(8))
+    assert sorted(c for p in plan2 for c in p) == allowed
+    # restricted mask: only what the process may use is handed out
+    plan3 = parallel.plan_rank_cpus(list(range(16, 48)), 2, [list(range(32)), list(range(32, 64))])
+    assert plan3 == [list(range(16, 32)), list(range(32, 48))]
+    # no topology, or one node = all CPUs: contiguous by rank
+    assert parallel.plan_rank_cpus(allowed, 4, None) == [list(range(16 * r, 16 * r + 16)) for r in range(4)]
+    assert parallel.plan_rank_cpus(allowed, 4, [allowed] * 4) == [list(range(16 * r, 16 * r + 16)) for r in range(4)]
+    # a rank with unknown topology sends everyone to the contiguous rule (no core handed out twice)
+    plan4 = parallel.plan_rank_cpus(allowed, 4, [list(range(32)), None, list(range(32, 64)), list(range(32, 64))])
+    assert sorted(c for p in plan4 for c in p) == allowed
