@@ -804,10 +804,10 @@ __host__ __device__ inline int q_stride(int H) { return H | 1; }     // float4 p
 #ifndef OCD_Q_CS
 #define OCD_Q_CS 1
 #endif
-__host__ __device__ inline int q2_stride(int H) { return (H + 1) | 1; }                 // float2 per thread row
+__host__ __device__ inline int q2_stride(int H) { return (H - 1) | 1; }                 // float2 per thread row: steps 1 .. H-1 (entry t at index t-1)
 __host__ __device__ inline int q_thread_floats(int H) { return 4 * q_stride(H) + (OCD_Q_CS ? 2 * q2_stride(H) : 0); }
 
-template <int HT, int NOT_, int LT, int VM, bool SF>
+template <int HT, int NOT_, int LT, int VM, bool SF, bool LIN = false>
 __device__ __forceinline__ void forward_sweep_q(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                 float th0, float sn0, float cs0, const float *oth, int P,
                                                 const Traj<HT> &u, float *sv, float *sc, float *ss, float4 *q,
@@ -837,26 +837,30 @@ __device__ __forceinline__ void forward_sweep_q(const KParams &k, const GradW &w
         th = fmaf(oc, k.dt, th);
         Mth<false>::sincos_(th, sn, cs);
         float gx, hy, ke, unused;
-        feature_grad<NOT_, LT, false, false, VM>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P, gx, hy, ke,
-                                                 unused, 0.0f, flag);
+        if (LIN)        // the slab holds (x0, dx, y0, dy) per other car: the position after t+1 steps is x0 + (t+1) dx
+            feature_grad<NOT_, LT, false, true, VM, true, true>(k, w, x, y, v, sn, cs, oth, 4 * P, P, gx, hy, ke, unused,
+                                                                (float)(t + 1), flag);
+        else
+            feature_grad<NOT_, LT, false, false, VM>(k, w, x, y, v, sn, cs, oth + (size_t)t * NO * 2 * P, 2 * P, P, gx, hy,
+                                                     ke, unused, 0.0f, flag);
         q[t] = make_float4(dist, gx, hy, ke);
     }
     sv[HT] = v; sc[HT] = cs; ss[HT] = sn;
 }
 
-template <int HT, int NOT_, int LT, int LAT>
+template <int HT, int NOT_, int LT, int LAT, bool LIN = false>
 __device__ __forceinline__ void sgd_iteration_q(const KParams &k, const GradW &w, float x0, float y0, float v0,
                                                 float th0, float sn0, float cs0, const float *oth, int P,
                                                 Traj<HT> &u, float4 *q, float2 *q2) {
     float sv[HT + 1], sc[HT + 1], ss[HT + 1];
     bool flag = false;
     if (LAT != 0) {
-        forward_sweep_q<HT, NOT_, LT, 1, (OCD_Q_SF != 0 || (LAT == 2 && NOT_ >= 3))>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P,
-                                                                                    u, sv, sc, ss, q, q2, flag);
+        forward_sweep_q<HT, NOT_, LT, 1, (OCD_Q_SF != 0 || (LAT == 2 && NOT_ >= 3)), LIN>(k, w, x0, y0, v0, th0, sn0, cs0, oth,
+                                                                                         P, u, sv, sc, ss, q, q2, flag);
         if (__any_sync(OCD_FULL, flag))
-            forward_sweep_q<HT, NOT_, LT, 0, false>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
+            forward_sweep_q<HT, NOT_, LT, 0, false, LIN>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
     } else {
-        forward_sweep_q<HT, NOT_, LT, 0, false>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
+        forward_sweep_q<HT, NOT_, LT, 0, false, LIN>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, sv, sc, ss, q, q2, flag);
     }
     float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
     const float c1 = -2.0f * k.mu * k.dt, c2 = -k.mu * k.dt2;
@@ -895,7 +899,7 @@ __device__ __forceinline__ void sgd_iteration_q(const KParams &k, const GradW &w
     }
 }
 
-template <int HT, int NOT_, int LT, int LAT>
+template <int HT, int NOT_, int LT, int LAT, bool LIN = false>
 __device__ __forceinline__ float solve_start_q(const KParams &k, const GradW &w, const float *wraw, int ws, float x0,
                                                float y0, float v0, float th0, const float *oth, int P, Traj<HT> &u,
                                                float4 *q, float2 *q2) {
@@ -903,8 +907,8 @@ __device__ __forceinline__ float solve_start_q(const KParams &k, const GradW &w,
     Mth<false>::sincos_(th0, sn0, cs0);
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it)
-        sgd_iteration_q<HT, NOT_, LT, LAT>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, q, q2);
-    return -rollout_reward<HT, LT, false, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+        sgd_iteration_q<HT, NOT_, LT, LAT, LIN>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, q, q2);
+    return -rollout_reward<HT, LT, false, Traj<HT>, LIN>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 
 // ---------------------------------------------------------------------------------------------

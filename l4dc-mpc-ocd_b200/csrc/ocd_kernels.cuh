@@ -192,7 +192,15 @@ __device__ __forceinline__ void stage_world_tile(float *tile, const float *world
 
 // lin: the slab holds (x0, dx, y0, dy) per other car instead of a position per horizon step
 // (worth its two extra FFMA per car and step only once the per-step slab would crowd out resident blocks)
-__host__ __device__ inline bool slab_is_linear(bool seg, bool precise, int other_mode, int H, int NO) {
+// The Q kernels (qk) can take it too (-DOCD_Q_LIN=1): their per-step slab is what stands between five and six resident
+// blocks per SM.  Measured (profiles/tuning/r02_ab_qlin.log, H = 15, 2^20 problems): six blocks are SLOWER, 17.0 vs
+// 16.0 ms -- the unrolled 15-step sweep is bound by instruction fetch, and more warps at different addresses make that
+// worse -- so it is off.
+#ifndef OCD_Q_LIN
+#define OCD_Q_LIN 0
+#endif
+__host__ __device__ inline bool slab_is_linear(bool seg, bool precise, int other_mode, int H, int NO, bool qk = false) {
+    if (qk) return OCD_Q_LIN && !precise && other_mode == 0;
     return seg && !precise && other_mode == 0 && (H * NO >= 100 || H >= 32);
 }
 
@@ -275,7 +283,7 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     constexpr int P = kP;     // compile-time, so every slab access is base + immediate
     constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT, NOT_);   // runtime or long horizon: segmented adjoint, controls in shared memory
     constexpr bool QK = OCD_IS_Q(HT, NOT_) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
-    const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO);
+    const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO, QK);
     const Smem m = carve(smem_raw, k, P, false, SEGK, lin, QK);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
@@ -327,9 +335,11 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
                                                                                   m.oth + p, P, s, speed, us, ck);
     } else if constexpr (QK) {
         init_start<HT>(k, s, speed, u);
-        loss = solve_start_q<HT, NOT_, LT, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u,
-                                                m.q + (size_t)threadIdx.x * q_stride(HT),
-                                                reinterpret_cast<float2 *>(m.q + (size_t)k.S * P * q_stride(HT)) + (size_t)threadIdx.x * q2_stride(HT));
+        float4 *q = m.q + (size_t)threadIdx.x * q_stride(HT);
+        // (cos, sin) rows behind the float4 rows; entry t of a row sits at index t - 1 (steps 1 .. HT-1 are stored)
+        float2 *q2 = reinterpret_cast<float2 *>(m.q + (size_t)k.S * P * q_stride(HT)) + (size_t)threadIdx.x * q2_stride(HT) - 1;
+        loss = lin ? solve_start_q<HT, NOT_, LT, LAT, true>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u, q, q2)
+                   : solve_start_q<HT, NOT_, LT, LAT, false>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u, q, q2);
     } else {
         init_start<(SEGK ? 1 : HT)>(k, s, speed, u);
         loss = solve_start<(SEGK ? 1 : HT), NOT_, LT, PRECISE, LAT>(k, gw, m.wraw + p, P, x0, y0, v0, th0, m.oth + p, P, u);
@@ -767,7 +777,7 @@ template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     constexpr bool SEGK = HT == 0 || OCD_IS_SEGC(HT, NOT_);
     const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, SEGK,
-                                     slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO),
+                                     slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO, OCD_IS_Q(HT, NOT_) && !PRECISE),
                                      OCD_IS_Q(HT, NOT_) && !PRECISE) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     constexpr bool ANY_LAT = HAS_LAT || (HT == 0 && !PRECISE);
