@@ -421,8 +421,11 @@ def horizons_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier,
     medium-horizon (Q) and long-horizon (segmented) kernels.  Same accounting as the headline: all ranks'
     solves / slowest rank's time."""
     rows = []
-    for H, B in ((15, 262144), (50, 65536)):
-        p, ms, finite = _timed_solve(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, H, 2, B, 5)
+    # 2^20 problems per GPU like the headline (BASELINE configs[4]'s largest batch): 32 768 blocks are hundreds of
+    # waves, so the tail of the last wave does not colour the figure (at 65 536 problems H = 50 runs 3.46 waves of
+    # four blocks per SM and loses 13 % to the tail alone; the small batches are in the `sweep` key)
+    for H, B, reps in ((15, 1048576, 4), (50, 1048576, 2)):
+        p, ms, finite = _timed_solve(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, H, 2, B, reps)
         fl = synthetic.flops_per_solve(H, 2, 3)
         rows.append({"horizon": H, "problems_per_gpu": B, "lr": p.lr, "ms_per_launch": ms,
                      "solves_per_sec": B * world_size / (ms * 1e-3), "kernel_form": ocd.kernel_form(p, B),

@@ -72,9 +72,12 @@ namespace ocd {
 #ifndef OCD_SEGC_SEG
 #define OCD_SEGC_SEG 5      // steps per segment of the long compile-time horizons (checkpoint rows are sized for 5)
 #endif
+#ifndef OCD_WIDE_REGS1
+#define OCD_WIDE_REGS1 128      // wide form, one other car (tuning knob)
+#endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? 128 : 168) : ((HT) > 0 ? 72 : 96))))
+    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? OCD_WIDE_REGS1 : 168) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
