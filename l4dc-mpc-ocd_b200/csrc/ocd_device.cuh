@@ -913,23 +913,26 @@ __device__ __forceinline__ float solve_start_q(const KParams &k, const GradW &w,
 
 // ---------------------------------------------------------------------------------------------
 // Time-parallel solve: the lowest-latency path, for batches so small that even the latency variant
-// leaves the GPU idle (the reference's real configurations: 45-180 episodes).  kTG = 8 consecutive
-// lanes share one (problem, start); lane t owns horizon step t (HT <= kTG; spare lanes shadow the
-// last step).  Per iteration the lanes all-gather the controls (2 HT shuffles), every lane rolls the
-// cheap dynamics for the whole horizon, evaluates the expensive feature gradient for ITS step only,
-// the gradients are all-gathered (4 HT shuffles) and every lane runs the short reverse sweep, keeping the
-// update of its own control.  Same formulas in the same order as sgd_iteration, so the result is bit
+// leaves the GPU idle (the reference's real configurations: 45-180 episodes).  TG consecutive lanes share one
+// (problem, start) -- TG = 8 for horizons up to 8, 16 for horizons up to 16 (tp_lanes) -- and lane t owns horizon
+// step t (HT <= TG; spare lanes shadow the last step).  Per iteration the lanes all-gather the controls (2 HT
+// shuffles), every lane rolls the cheap dynamics for the whole horizon, evaluates the expensive feature gradient for
+// ITS step only, the gradients are all-gathered (3 HT shuffles) and every lane runs the short reverse sweep, keeping
+// the update of its own control.  Same formulas in the same order as sgd_iteration, so the result is bit
 // for bit the one of the other kernels; the dependent chain per iteration shrinks from H feature
 // evaluations to one.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kTG = 8;
+static constexpr int kTG = 8;                 // lanes per (problem, start) for horizons up to 8
+static constexpr int kTGMax = 16;             // ... and for horizons 9 .. 16
+__host__ __device__ constexpr int tp_lanes(int HT) { return HT <= kTG ? kTG : kTGMax; }
 
 template <int HT, int NOT_, int LT>
 __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w, const float *wraw, int ws,
                                                 float x0, float y0, float v0, float th0, const float *oth, int P,
                                                 int t, float a_init, float w_init, Traj<HT> &u) {
-    static_assert(HT > 0 && HT <= kTG, "time-parallel solve: one lane per horizon step");
+    static_assert(HT > 0 && HT <= kTGMax, "time-parallel solve: one lane per horizon step");
     constexpr int NO = NOT_;
+    constexpr int TG = tp_lanes(HT);
     const int tt = t < HT ? t : HT - 1;
     float ua = a_init, uw = w_init;                      // this lane's control: step tt
     float sn0, cs0;
@@ -942,8 +945,8 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
         float A[HT], W[HT], sv[HT + 1], sc[HT + 1], ss[HT + 1], sd[HT];    // [j]: at the state before step j
 #pragma unroll
         for (int j = 0; j < HT; ++j) {
-            A[j] = __shfl_sync(OCD_FULL, ua, j, kTG);
-            W[j] = __shfl_sync(OCD_FULL, uw, j, kTG);
+            A[j] = __shfl_sync(OCD_FULL, ua, j, TG);
+            W[j] = __shfl_sync(OCD_FULL, uw, j, TG);
         }
         float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
         float mx_ = 0.0f, my_ = 0.0f, mv_ = 0.0f, msn = 0.0f, mcs = 0.0f;
@@ -974,9 +977,9 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
         float GX[HT], HY[HT], KE[HT];
 #pragma unroll
         for (int j = 0; j < HT; ++j) {
-            GX[j] = __shfl_sync(OCD_FULL, gx, j, kTG);
-            HY[j] = __shfl_sync(OCD_FULL, hy, j, kTG);
-            KE[j] = __shfl_sync(OCD_FULL, ke, j, kTG);
+            GX[j] = __shfl_sync(OCD_FULL, gx, j, TG);
+            HY[j] = __shfl_sync(OCD_FULL, hy, j, TG);
+            KE[j] = __shfl_sync(OCD_FULL, ke, j, TG);
         }
         float lx = 0.0f, ly = 0.0f, lv = 0.0f, lth = 0.0f;
         float ld_ = 0.0f, mv_t = 0.0f, mth_t = 0.0f;         // the three adjoint terms of this lane's own step
@@ -1005,8 +1008,8 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
     }
 #pragma unroll
     for (int j = 0; j < HT; ++j) {
-        u.ua[j] = __shfl_sync(OCD_FULL, ua, j, kTG);
-        u.uw[j] = __shfl_sync(OCD_FULL, uw, j, kTG);
+        u.ua[j] = __shfl_sync(OCD_FULL, ua, j, TG);
+        u.uw[j] = __shfl_sync(OCD_FULL, uw, j, TG);
     }
     return -rollout_reward<HT, LT, false, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }

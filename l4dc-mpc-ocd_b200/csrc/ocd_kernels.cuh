@@ -512,11 +512,13 @@ k_episode(const __grid_constant__ KParams k, const __grid_constant__ ocd_scenari
 }
 
 // ---------------------------------------------------------------------------------------------
-// Time-parallel variants (solve_start_tp): kTG = 8 lanes per (problem, start), kTP = 4 problems per
-// block, thread = ((s * kTP + p) * kTG + t): warp s still runs start s, of 4 problems x 8 step-lanes.
+// Time-parallel variants (solve_start_tp): TG = 8 lanes per (problem, start) and 4 problems per block for horizons
+// up to 8, 16 lanes and 2 problems for horizons 9 .. 16 (k_solve_tp only: the episode kernels are instantiated for
+// H = 5 / 6); thread = ((s * P + p) * TG + t): warp s still runs start s, of P problems x TG step-lanes.
 // Everything but the solve itself is k_solve / k_episode with the per-problem work on lane t == 0.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kTP = 4;
+static constexpr int kTP = 4;                                       // problems per block with 8 lanes per (problem, start)
+__host__ __device__ constexpr int tp_problems(int HT) { return 32 / tp_lanes(HT); }   // 4, or 2 with 16 lanes
 
 __device__ __forceinline__ void tp_start_controls(const KParams &k, int s, float cur_speed, float &a0, float &w0) {
     a0 = (s >= 3) ? __fmul_rn(k.mu, __fmul_rn(cur_speed, cur_speed)) : 0.0f;      // naive_planner.py:107-118
@@ -525,11 +527,11 @@ __device__ __forceinline__ void tp_start_controls(const KParams &k, int s, float
 }
 
 template <int HT, int NOT_, int LT>
-__global__ void __launch_bounds__(6 * kTP * kTG, 1) k_solve_tp(const __grid_constant__ KParams k, const SolveArgs a) {
+__global__ void __launch_bounds__(6 * 32, 1) k_solve_tp(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
-    constexpr int P = kTP;
+    constexpr int P = tp_problems(HT), TG = tp_lanes(HT);
     const Smem m = carve(smem_raw, k, P, false, false, false);
-    const int t = threadIdx.x % kTG, g = threadIdx.x / kTG, p = g % P, s = g / P;
+    const int t = threadIdx.x % TG, g = threadIdx.x / TG, p = g % P, s = g / P;
     const long long b_raw = (long long)blockIdx.x * P + p;
     const bool live = b_raw < a.B;
     const long long b = live ? b_raw : a.B - 1;
@@ -745,9 +747,9 @@ inline int forced_form() {
     return e[0] == 'l' ? kFormLatency : (e[0] == 'w' ? kFormWide : kFormAuto);
 }
 inline long long batch_warps(long long B, int P, int S) { return ((B + P - 1) / P) * S; }
-inline bool tiny_batch(long long B, int S) {
+inline bool tiny_batch(long long B, int S, int P = kTP) {      // P: problems per warp of the time-parallel form
     const int f = forced_form();
-    return f ? f == kFormTp : batch_warps(B, kTP, S) <= 800;
+    return f ? f == kFormTp : batch_warps(B, P, S) <= 800;
 }
 // -> 0 throughput, 1 latency, 2 wide.
 inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode,
@@ -771,7 +773,8 @@ inline int choose_form(const KParams &k, long long B, bool episode) {
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;          // compile-time horizon and car count
     constexpr bool SEG_LAT = HT == 0 && !PRECISE;                       // segmented kernels (solve only)
     constexpr bool REGRES = HT > 0 && !OCD_IS_Q(HT, NOT_) && !OCD_IS_SEGC(HT, NOT_);  // register-resident (short) horizons
-    if (HAS_LAT && HT <= kTG && tiny_batch(B, k.S)) return 3;
+    // time-parallel: episodes up to 8 steps of horizon (the instantiated episode kernels), solves up to 16
+    if (HAS_LAT && HT <= (episode ? kTG : kTGMax) && tiny_batch(B, k.S, tp_problems(HT > 0 ? HT : 1))) return 3;
     if (episode) return pick_form(B, kP, k.S, HAS_LAT, HAS_LAT && NOT_ == 1, NOT_ == 1, true);
     return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, REGRES && NOT_ == 1, false, REGRES && NOT_ >= 3);
 }
@@ -785,10 +788,11 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
     constexpr bool ANY_LAT = HAS_LAT || (HT == 0 && !PRECISE);
     const int form = choose_form<HT, NOT_, LT, PRECISE>(k, a.B, false);
-    if constexpr (HAS_LAT && HT <= kTG) {
+    if constexpr (HAS_LAT && HT <= kTGMax) {
         if (form == 3) {
-            const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, kTP, false, false, false) * sizeof(float);
-            k_solve_tp<HT, NOT_, LT><<<(unsigned)((a.B + kTP - 1) / kTP), k.S * kTP * kTG, tb, st>>>(k, a);
+            constexpr int TPP = tp_problems(HT);
+            const size_t tb = smem_floats(k.H, k.NO, k.K, k.S, TPP, false, false, false) * sizeof(float);
+            k_solve_tp<HT, NOT_, LT><<<(unsigned)((a.B + TPP - 1) / TPP), k.S * 32, tb, st>>>(k, a);
             return cuda_status();
         }
     }

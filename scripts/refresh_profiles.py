@@ -16,8 +16,9 @@ ROOT = Path(__file__).resolve().parent.parent
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
 tag, sweep, bench, ref = sys.argv[1:5]
 scaling_logs = sys.argv[5:]
+R = tag.split("_")[0] if tag.startswith("r0") else "r01"      # round prefix of the tracked files (r01, r02, ...)
 
-shutil.copy(G / f"launches_{tag}.csv", P / "r01_launches.csv")
+shutil.copy(G / f"launches_{tag}.csv", P / f"{R}_launches.csv")
 rows = [r for r in csv.reader(open(G / f"launches_{tag}.csv")) if r and r[0].isdigit()]
 agg = collections.OrderedDict()
 for r in rows:
@@ -25,7 +26,7 @@ for r in rows:
     a[0] += 1
     a[1] += float(r[-1].replace(",", "")) / 1e6
 tot = sum(v[1] for v in agg.values())
-with open(P / "r01_launch_shares.txt", "w") as f:
+with open(P / f"{R}_launch_shares.txt", "w") as f:
     f.write("# python bench.py --steps 5 --warmup 3 --no-extras under `ncu --metrics gpu__time_duration.sum "
             "--clock-control none`\n# launches  total_ms  share  kernel\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -40,15 +41,16 @@ def summ(rep, out, title):
     return o
 
 
-main = summ(G / f"prof_solve_{tag}.ncu-rep", P / "r01_k_solve_ncu_summary.txt",
+main = summ(G / f"prof_solve_{tag}.ncu-rep", P / f"{R}_k_solve_ncu_summary.txt",
             "k_solve<5,1,3,fast,wide> at the bench shape (B = 2^20, H=5, 2 cars)")
-for name, title in (("h5c6", "k_solve<5,5,3,fast,wide+step fence>: sweep point H=5, 6 cars, B = 262144"),
-                    ("h15c2", "k_solve<0,1,3,fast,wide> (segmented adjoint): sweep point H=15, 2 cars, B = 262144"),
-                    ("h50c2", "k_solve<0,1,3,fast,wide> (segmented adjoint): sweep point H=50, 2 cars, B = 65536")):
+for name, title in (("h5c6", "k_solve<5,5,3,fast,wide+step fence>: sweep point H=5, 6 cars, B = 2^20"),
+                    ("h15c2", "k_solve<15,1,3,fast,wide> (Q kernel: saved step data through shared memory): sweep point H=15, 2 cars, B = 2^20"),
+                    ("h15c6", "k_solve<15,5,3,fast,wide> (constant-segment-count adjoint): sweep point H=15, 6 cars, B = 2^20"),
+                    ("h50c2", "k_solve<50,1,3,fast,wide> (constant-segment-count adjoint): sweep point H=50, 2 cars, B = 2^20")):
     rep = G / f"prof_{tag}_{name}.ncu-rep"
     if rep.exists():
-        summ(rep, P / f"r01_k_solve_{name}_ncu_summary.txt", title)
-shutil.copy(G / sweep, P / "r01_sweep.json")
+        summ(rep, P / f"{R}_k_solve_{name}_ncu_summary.txt", title)
+shutil.copy(G / sweep, P / f"{R}_sweep.json")
 
 rd = wr = 0.0
 for line in main.splitlines():
@@ -70,11 +72,11 @@ def last_json(path):
     return json.loads(open(G / path).read().strip().splitlines()[-1])
 
 
-d = {"note": "round 1 final kernels; full 1-GPU line, the --impl reference arm from the same box, and the 1/2/4/8-GPU "
-             "lines (torchrun, one rank per GPU)",
+d = {"note": f"{R} kernels; full 1-GPU line, the --impl reference arm from the same box, and the multi-GPU "
+             "lines given (torchrun, one rank per GPU)",
      "bench": last_json(bench), "reference_arm": last_json(ref)}
 lines = [d["bench"]] + [last_json(x) for x in scaling_logs]
 d["scaling"] = [{"n_gpus": x["n_gpus"], "value": x["value"], "ms_per_step": x["ms_per_step"], "e2e": x["e2e"]["value"],
                  "cmaes_ms_per_generation": x["cmaes"]["ms_per_generation"], "clocks": x["clocks"]} for x in lines]
-json.dump(d, open(P / "r01_bench.json", "w"), indent=1)
+json.dump(d, open(P / f"{R}_bench.json", "w"), indent=1)
 print("profiles/ refreshed from tag", tag)

@@ -543,23 +543,26 @@ def test_full_size_properties(engine):
 
 
 def test_kernel_forms_agree(engine, monkeypatch):
-    """Every shape has up to four kernel forms, picked by batch size: time-parallel (8 lanes per start), latency
+    """Every shape has up to four kernel forms, picked by batch size: time-parallel (8 lanes per start; 16 for the
+    compile-time H = 15), latency
     (straight-line forward sweep), wide (the same at 128 registers, one-other-car shapes) and throughput
     (vote-guarded).  The same problems must get the same answer whichever runs: each form is forced through
     OCD_KERNEL_FORM on the same 3 000 problems, and the automatic choice is checked at three batch sizes.
     Covers the finite_horizon shape, the replanning shape (two other cars, two lanes), H = 6, the six-start set,
-    many cars, and the segmented kernels (H = 12, 15).  Forms whose basic blocks differ (the segmented forms, the
+    many cars, the medium-horizon Q kernels (H = 15), the constant-segment-count kernels (H = 15 with two other cars,
+    H = 50) and the runtime-horizon segmented kernels (H = 12).  Forms whose basic blocks differ (the segmented forms, the
     step-fenced wide form for four and more cars) fuse multiply-adds differently: same plans to tolerance, up to
     ill-conditioned problems; all other forms are bit-identical."""
     stats, ok = [], True
     for C, lane_x, ts, H, extra in ((2, (-0.1, 0.0, 0.1), 1.0, 5, False), (3, (-0.05, 0.05), 1.2, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
                                     (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False),
-                                    (2, (-0.1, 0.0, 0.1), 1.0, 15, False), (5, (-0.1, 0.0, 0.1), 1.0, 12, False)):
-        B, n = (32768 if extra else 65536), 3000
+                                    (2, (-0.1, 0.0, 0.1), 1.0, 15, False), (5, (-0.1, 0.0, 0.1), 1.0, 12, False),
+                                    (3, (-0.1, 0.0, 0.1), 1.0, 15, False), (2, (-0.1, 0.0, 0.1), 1.0, 50, False)):
+        B, n = (32768 if (extra or H == 50) else 65536), 3000
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
         p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra,
-                              lr=0.1 if H <= 6 else 0.03)
+                              lr=0.1 if H <= 6 else (0.03 if H <= 15 else 0.0003))
 
         def solve(m):
             return engine.solve(p, batch["world"][:m], batch["weights"], weight_idx=batch["weight_idx"][:m],
