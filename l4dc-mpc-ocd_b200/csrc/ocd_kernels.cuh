@@ -749,7 +749,9 @@ inline int forced_form() {
 inline long long batch_warps(long long B, int P, int S) { return ((B + P - 1) / P) * S; }
 inline bool tiny_batch(long long B, int S, int P = kTP) {      // P: problems per warp of the time-parallel form
     const int f = forced_form();
-    return f ? f == kFormTp : batch_warps(B, P, S) <= 800;
+    // 8 lanes per start: up to ~800 warps; 16 lanes (H = 9..16) up to ~1 800: H = 15, 720 problems 0.146 ms against
+    // 0.207 ms for the latency form, 1 440 problems 0.191 against 0.186 (profiles/tuning/r02_tp16.log)
+    return f ? f == kFormTp : batch_warps(B, P, S) <= (P == kTP ? 800 : 1800);
 }
 // -> 0 throughput, 1 latency, 2 wide.
 inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode,
