@@ -155,6 +155,19 @@ int ocd_feature_jacobian_batch(const ocd_params *p, const float *world /*[C][4][
                                float *phi_sum /*[K][B]*/, float *jac /*[K][H][2][B]*/,
                                int64_t B, void *stream);
 
+/* Hessians of the horizon-summed features with respect to the controls: what the reference's second-order inverse
+ * optimal control takes from TensorFlow as t.jacobian(gradients, controls)
+ * (interact_drive/reward_design/second_order_ioc.py:80-152, LocalCIOC.compute_total_augmented_loss).  The reward is
+ * linear in the weights, so the Hessian of the reward is sum_k w_k hess[k] and CIOC's likelihood and its weight
+ * gradient need nothing beyond these K matrices and ocd_feature_jacobian_batch's K rows.  Exact second derivatives
+ * (hyper-dual arithmetic in float32, libdevice transcendentals), TensorFlow's branch conventions at clip / min / max /
+ * where; other cars as in ocd_reward_grad_batch.  Output: hess [K][2H][2H][B], symmetric in the two control
+ * indices (flat index 2 t + c for control c of step t). */
+int ocd_feature_hessian_batch(const ocd_params *p, const float *world /*[C][4][B]*/,
+                              const float *controls /*[H][2][B]*/,
+                              const float *other_controls, int64_t Bo,
+                              float *hess /*[K][2H][2H][B]*/, int64_t B, void *stream);
+
 /* NaivePlanner.generate_plan (interact_drive/planner/naive_planner.py:81-164) + Keras SGD
  * (call sites :28,:153): S starts x n_iter gradient steps, final loss per start, first-minimum
  * argmin.  cur_speed ([B] or NULL -> world's robot speed) feeds the extra_inits starts (:114-116).
@@ -204,6 +217,14 @@ int ocd_episode_batch(const ocd_params *p, const ocd_scenario *sc,
 typedef struct ocd_ctx ocd_ctx;
 int  ocd_ctx_create(int device, ocd_ctx **out);
 void ocd_ctx_destroy(ocd_ctx *ctx);
+
+/* Page-lock a caller-owned host array in place (cudaHostRegister) / undo it.  A steady-state caller that reuses its
+ * ordinary (pageable) input and output arrays registers them once; the *_host calls then copy from / into them
+ * directly, exactly as for arrays allocated page-locked, instead of staging every call through the context's pinned
+ * area with host memcpys (which is what bounds eight ranks sharing one host's cores).  The caller must unregister before
+ * freeing the memory.  -> OCD_OK, OCD_EINVAL (null / zero bytes) or OCD_ECUDA (not lockable, already registered). */
+int ocd_host_register(void *ptr, size_t bytes);
+int ocd_host_unregister(void *ptr);
 
 int ocd_solve_batch_host(ocd_ctx *ctx, const ocd_params *p, const float *world,
                          const float *other_controls, int64_t Bo,

@@ -7,7 +7,7 @@
 import importlib as _importlib
 
 __all__ = ["Engine", "HostContext", "PlannerParams", "Scenario", "MATH_FAST", "MATH_PRECISE", "OPT_SGD", "OPT_LBFGS",
-           "device_count", "kernel_form"]
+           "device_count", "kernel_form"]           # + OcdError, OcdCudaError (from _native, resolved below)
 
 
 def __getattr__(name):
@@ -19,6 +19,8 @@ def __getattr__(name):
         return getattr(_importlib.import_module(__name__ + ".engine"), name)
     if name in ("_native", "engine"):
         return _importlib.import_module(__name__ + "." + name)
+    if name in ("OcdError", "OcdCudaError"):
+        return getattr(_importlib.import_module(__name__ + "._native"), name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
@@ -38,7 +40,9 @@ def install_as_reference() -> None:
                  "interact_drive.car.fixed_plan_car", "interact_drive.car.planner_car",
                  "interact_drive.car.linear_reward_car", "interact_drive.planner",
                  "interact_drive.planner.car_planner", "interact_drive.planner.naive_planner",
-                 "interact_drive.reward_design", "interact_drive.reward_design.mpc_ord", "experiments",
+                 "interact_drive.reward_design", "interact_drive.reward_design.mpc_ord",
+                 "interact_drive.reward_design.first_order_ioc", "interact_drive.reward_design.second_order_ioc",
+                 "experiments",
                  "experiments.merging", "experiments.local_opt_scenario", "experiments.replanning_world",
                  "experiments.run_mpc_ord"):
         sys.modules[name] = importlib.import_module(pkg + "." + name)

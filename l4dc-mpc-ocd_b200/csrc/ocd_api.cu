@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "ocd_kernels.cuh"
+#include "ocd_hessian.cuh"
 
 namespace ocd {
 
@@ -641,6 +642,21 @@ int ocd_feature_jacobian_batch(const ocd_params *p, const float *world, const fl
     return cuda_status();
 }
 
+int ocd_feature_hessian_batch(const ocd_params *p, const float *world, const float *controls,
+                              const float *other_controls, int64_t Bo, float *hess, int64_t B, void *stream) {
+    KParams k;
+    int rc = digest(p, k);
+    if (rc) return rc;
+    if (B == 0) return OCD_OK;
+    if (!world || !controls || !hess || B < 0) return OCD_EINVAL;
+    if (k.other_mode == 1 && (!other_controls || (Bo != 1 && Bo != B))) return OCD_EINVAL;
+    const int n = 2 * k.H;
+    if (n * (n + 1) / 2 > 65535) return OCD_EUNSUP;
+    const dim3 grid((unsigned)((B + 127) / 128), (unsigned)(n * (n + 1) / 2));     // one slice per control pair i <= j
+    k_feature_hessian<<<grid, 128, 0, (cudaStream_t)stream>>>(k, world, controls, other_controls, Bo, hess, B);
+    return cuda_status();
+}
+
 int ocd_solve_batch(const ocd_params *p, const float *world, const float *other_controls, int64_t Bo,
                     const float *weights, int64_t Bw, const int32_t *weight_idx, const float *cur_speed,
                     float *plan, float *losses, int32_t *best, float *all_plans, int64_t B, void *stream) {
@@ -782,6 +798,24 @@ struct Arena {
 };
 
 // true when `ptr` is page-locked host memory the copy engines can read or write directly
+int ocd_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return OCD_EINVAL;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return OCD_ECUDA;
+    }
+    return OCD_OK;
+}
+
+int ocd_host_unregister(void *ptr) {
+    if (!ptr) return OCD_EINVAL;
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return OCD_ECUDA;
+    }
+    return OCD_OK;
+}
+
 static bool is_pinned(const void *ptr) {
     if (!ptr) return false;
     cudaPointerAttributes a;

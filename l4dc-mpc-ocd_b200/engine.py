@@ -349,6 +349,28 @@ class Engine:
         self._kernel_launches += 1 if B else 0
         return phi.t().contiguous(), jac.permute(3, 0, 1, 2).contiguous()
 
+    def feature_hessian(self, p: PlannerParams, world, controls, other_controls=None) -> torch.Tensor:
+        """world [B, C, 4]; controls [B, H, 2] -> hess [B, K, 2H, 2H]: the Hessian of every horizon-summed feature
+        with respect to the flattened controls (index 2 t + c).  The reward's Hessian is sum_k w_k hess[:, k]."""
+        ws = self._world(p, world)
+        B = ws.shape[-1]
+        u = torch.as_tensor(controls, dtype=torch.float32, device=self.device)
+        if u.dim() == 2:
+            u = u.unsqueeze(0)
+        if tuple(u.shape) != (B, p.H, 2):
+            raise ValueError(f"controls must have shape [{B}, {p.H}, 2], got {tuple(u.shape)}")
+        us = u.permute(1, 2, 0).contiguous()
+        oc, Bo = self._other_controls(p, other_controls, B)
+        n = 2 * p.H
+        hess = torch.empty((p.K, n, n, B), dtype=torch.float32, device=self.device)
+        ps = p.c_struct()
+        with torch.cuda.device(self.device):
+            rc = N.lib.ocd_feature_hessian_batch(C.addressof(ps), _ptr(ws), _ptr(us), _ptr(oc), Bo, _ptr(hess), B,
+                                                 self._stream())
+        N.check(rc, "ocd_feature_hessian_batch")
+        self._kernel_launches += 1 if B else 0
+        return hess.permute(3, 0, 1, 2).contiguous()
+
     def features(self, p: PlannerParams, world) -> torch.Tensor:
         """world [B, C, 4] -> phi [B, K]."""
         ws = self._world(p, world)
@@ -463,6 +485,20 @@ class HostContext:
         t = torch.empty(tuple(shape), dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.int32,
                         pin_memory=True)
         return t.numpy()          # the array keeps the pinned storage alive (ndarray.base), and frees it with itself
+
+    @staticmethod
+    def register(array: np.ndarray) -> np.ndarray:
+        """Page-lock an ordinary numpy array in place (ocd_host_register): a caller that reuses its input / output
+        arrays registers them once and the host-buffer calls then copy from / into them directly, like arrays from
+        pinned_empty -- no staging memcpy.  Call unregister(array) before the array is freed."""
+        if not (isinstance(array, np.ndarray) and array.flags["C_CONTIGUOUS"]):
+            raise ValueError("register needs a C-contiguous numpy array")
+        N.check(N.lib.ocd_host_register(array.ctypes.data, array.nbytes), "ocd_host_register")
+        return array
+
+    @staticmethod
+    def unregister(array: np.ndarray) -> None:
+        N.check(N.lib.ocd_host_unregister(array.ctypes.data), "ocd_host_unregister")
 
     def solve_soa(self, p: PlannerParams, world: np.ndarray, weights: np.ndarray, weight_idx=None,
                   other_controls=None, cur_speed=None, out=None):

@@ -148,6 +148,20 @@ class NaivePlanner(CarPlanner):
         phi, jac = self.engine.feature_jacobian(p, st, as_f32(controls), other_controls=other_controls)
         return phi.cpu().numpy(), jac.cpu().numpy()
 
+    def feature_hessian_batch(self, init_states, controls, other_controls=None):
+        """init_states [B, C, 4] in WORLD car order, controls [B, H, 2] of the planning car -> hess [B, K, 2H, 2H]
+        (host array): the Hessian of every horizon-summed feature with respect to the flattened controls -- what the
+        reference's LocalCIOC takes from `t.jacobian(gradients, controls)` (reward_design/second_order_ioc.py:143-147);
+        one launch."""
+        st = as_f32(init_states)
+        if st.ndim != 3 or st.shape[1] != len(self.world.cars) or st.shape[2] != 4:
+            raise ValueError("init_states must have shape [B, %d, 4]" % len(self.world.cars))
+        st = st[:, self._order()]
+        if st.shape[1] == 1:
+            st = np.concatenate([st, np.broadcast_to(_PHANTOM, (st.shape[0], 1, 4))], axis=1)
+        p = self.params(other_mode=0 if other_controls is None else 1)
+        return self.engine.feature_hessian(p, st, as_f32(controls), other_controls=other_controls).cpu().numpy()
+
     def generate_plan_batch(self, init_states, weights=None, weight_idx=None, other_controls=None, cur_speed=None):
         """init_states [B, C, 4] in WORLD car order; weights [K] | [Bw, K] (+ weight_idx [B]);
         other_controls [B|1, C-1, H, 2] for the non-planning cars in world order.

@@ -82,6 +82,11 @@ def main():
         "pinned_first_control_only": lambda: ctx.solve_first_soa(p, world, w, weight_idx=idx, out=only, losses=False, best=False),
         "pageable_full_plans": lambda: ctx.solve_soa(p, pg[0], pg[1], weight_idx=pg[2], out=pg_out),
     }
+    rg = (np.array(world), np.array(w), np.array(idx))
+    rg_out = {k: np.zeros_like(v) for k, v in full.items()}
+    for a in list(rg) + list(rg_out.values()):
+        ocd.HostContext.register(a)
+    variants["registered_full_plans"] = lambda: ctx.solve_soa(p, rg[0], rg[1], weight_idx=rg[2], out=rg_out)
     # device-resident reference point
     eng = ocd.Engine(lr)
     dw = torch.as_tensor(b["world"], device=dev).permute(1, 2, 0).contiguous()

@@ -119,3 +119,84 @@ def test_ioc_drop_ins():
     assert abs(iloc.segment_loss(w_true, init, ctr, index=0) - np.sum((blocks[0].T @ w_true) ** 2)) < 1e-9
     with pytest.raises(ValueError):
         lin.total_jacobian(traj[:3])
+
+
+# ---- second order: feature Hessians (ocd_feature_hessian_batch) and LocalCIOC --------------------------------------
+@pytest.mark.parametrize("H,C,lanes,other_mode", [(5, 2, 3, 0), (5, 3, 2, 1), (7, 4, 3, 0)])
+def test_feature_hessian_vs_oracle_differences(engine, H, C, lanes, other_mode):
+    """hess[k] = d^2 (sum_t phi_k) / du du: compared with central differences of the oracle's float64 GRADIENT (weights
+    e_k), an independent route to the same matrix.  Symmetric by construction of the kernel; the comparison covers both
+    triangles."""
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import LocalCIOC  # noqa: F401  (importable on a GPU box)
+    B = 24
+    lane_x, batch, world, u = _inputs(B, H, C, lanes, 91 + H + C)
+    u = (0.5 * u).astype(np.float32)
+    oc = 0.3 * synthetic.make_other_controls(B, C, H) if other_mode else None
+    p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=lanes, other_mode=other_mode,
+                          target_speed=1.0 if lanes == 3 else 1.2)
+    hes = engine.feature_hessian(p, world, u, other_controls=oc).cpu().numpy()
+    n = 2 * H
+    assert hes.shape == (B, p.K, n, n)
+    assert np.array_equal(hes, hes.transpose(0, 1, 3, 2))
+    op = O.OracleParams(H=H, C=C, lane_x=lane_x, num_lanes=lanes, other_mode=other_mode, target_speed=p.target_speed)
+    eye = np.eye(p.K)
+    h = 1e-5
+    worst, checked, skipped = 0.0, 0, 0
+    for b in range(0, B, 2):
+        ocb = None if oc is None else oc[b].astype(np.float64)
+        w64, u64 = world[b].astype(np.float64), u[b].astype(np.float64)
+        for k_ in range(p.K):
+            ref = np.zeros((n, n))
+            for i in range(n):
+                e = np.zeros(n); e[i] = h
+                gp = O.mpc_reward(op, w64, u64 + e.reshape(H, 2), eye[k_], other_controls=ocb, dtype=np.float64)[1]
+                gm = O.mpc_reward(op, w64, u64 - e.reshape(H, 2), eye[k_], other_controls=ocb, dtype=np.float64)[1]
+                ref[i] = (np.asarray(gp) - np.asarray(gm)).reshape(n) / (2 * h)
+            # a kink of min / max / clip inside the differencing interval makes the difference quotient meaningless
+            # (the one-sided quotients disagree): skip those matrices, they are rare
+            g0 = np.asarray(O.mpc_reward(op, w64, u64, eye[k_], other_controls=ocb, dtype=np.float64)[1]).reshape(n)
+            asym = np.abs(ref - ref.T).max()
+            scale = max(1.0, np.abs(ref).max())
+            if asym > 1e-4 * scale:
+                skipped += 1
+                continue
+            worst = max(worst, np.abs(hes[b, k_] - ref).max() / scale)
+            checked += 1
+            assert np.all(np.isfinite(g0))
+    assert checked >= 0.85 * (checked + skipped), (checked, skipped)
+    assert worst <= 2e-3, worst
+
+
+def test_hessian_of_quadratic_features_is_exact(engine):
+    """Straight driving with zero steering: the lane features 10 (x - l)^2 do not depend on the accelerations at all
+    and the whole matrix of the far-away collision feature is zero -- exact zeros, not small numbers."""
+    H = 5
+    world = np.array([[[0.02, -0.9, 0.8, np.pi / 2], [0.1, 5.0, 0.5, np.pi / 2]]], np.float32)
+    u = np.zeros((1, H, 2), np.float32)
+    u[0, :, 0] = 0.3
+    hes = engine.feature_hessian(ocd.PlannerParams(), world, u).cpu().numpy()[0]
+    acc = np.arange(0, 2 * H, 2)
+    assert np.all(hes[5] == 0.0)                                   # collision: the other car is far outside the support
+    # the steering block of the speed feature (v sin th - ts)^2 is not zero
+    assert np.abs(hes[0][1::2, 1::2]).max() > 0.0
+    assert np.all(np.isfinite(hes))
+    assert np.abs(hes[1][np.ix_(acc, acc)]).max() < 1e-6            # lanes: heading exactly along y, acc moves y only
+
+
+def test_local_cioc_runs_on_a_planned_trajectory():
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import LocalCIOC
+    world, car, traj, w_true = _drive(T=8)
+    cioc = LocalCIOC(car, weight_norm=1., initial_weights=-np.ones(7))
+    G, Hm = cioc.trajectory_terms(traj)
+    T = len(traj)
+    assert G.shape == (7, 2 * T) and Hm.shape == (7, 2 * T, 2 * T)
+    # the rows are the first-order classes' columns, in the same order
+    blocks = np.concatenate(cioc.jacobian_blocks(traj), axis=-1)
+    np.testing.assert_allclose(G, blocks, rtol=0, atol=1e-12)
+    l0, s0 = cioc.compute_total_augmented_loss(cioc.weights, traj, theta_r=100.0, mu=10.0, lm=0.0)
+    assert np.isfinite(l0) and s0 > 0                               # a large theta_r makes -A positive definite
+    w = cioc.rationalize(traj, n_iter=60, tol=0.05, max_outer=6)
+    assert w.shape == (7,) and np.all(np.isfinite(w)) and abs(np.linalg.norm(w) - 1.0) < 1e-5
+    split = LocalCIOC(car, weight_norm=1., split_traj=True)
+    Gs, Hs = split.trajectory_terms(traj[:5])
+    assert Gs.shape == (7, 10) and Hs.shape == (7, 10, 10)

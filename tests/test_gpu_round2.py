@@ -300,3 +300,32 @@ def test_soa_entry_points_refuse_wrong_tensors(engine):
                 dict(world=ws.permute(1, 0, 2))):
         with pytest.raises(ValueError):
             engine.solve_soa(p, bad.get("world", ws), bad.get("weights", wt), wt.shape[1], bad.get("idx", idx))
+
+
+def test_registered_host_arrays_take_the_in_place_path():
+    """ocd_host_register page-locks a caller's ordinary arrays in place: same results as the staged path, and the
+    registration can be undone; registering twice is an error, not a crash."""
+    B = 20000
+    p = ocd.PlannerParams()
+    b = synthetic.make_batch(B, seed=8)
+    world = np.ascontiguousarray(b["world"].transpose(1, 2, 0))
+    w = np.ascontiguousarray(b["weights"].T)
+    idx = b["weight_idx"]
+    ctx = ocd.HostContext(0)
+    ref = ctx.solve_soa(p, world, w, weight_idx=idx)
+    ref = {k: np.array(v) for k, v in ref.items()}
+    out = dict(plan=np.zeros((p.H, 2, B), np.float32), losses=np.zeros((p.S, B), np.float32), best=np.zeros((B,), np.int32))
+    arrays = [world, w, idx] + list(out.values())
+    for a in arrays:
+        ocd.HostContext.register(a)
+    with pytest.raises(ocd.OcdCudaError):
+        ocd.HostContext.register(world)
+    got = ctx.solve_soa(p, world, w, weight_idx=idx, out=out)
+    for k in ref:
+        assert np.array_equal(ref[k], got[k])
+    for a in arrays:
+        ocd.HostContext.unregister(a)
+    got = ctx.solve_soa(p, world, w, weight_idx=idx, out=out)          # pageable again: staged path, same answer
+    for k in ref:
+        assert np.array_equal(ref[k], got[k])
+    ctx.close()

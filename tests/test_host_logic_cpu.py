@@ -240,7 +240,10 @@ def test_kernel_form_selection(monkeypatch):
     six = ocd.PlannerParams(C=6)                                        # step-fenced wide form: big batches only
     assert [ocd.kernel_form(six, B) for B in (500, 30000, 65536, 262144)] == \
         ["time-parallel", "latency", "throughput", "wide"]
-    assert [ocd.kernel_form(ocd.PlannerParams(H=15), B) for B in (100, 40000, 1 << 20)] == ["latency", "latency", "wide"]
+    # H = 15: the 16-lane time-parallel form up to ~1 800 warps (two problems x three starts per block)
+    assert [ocd.kernel_form(ocd.PlannerParams(H=15), B) for B in (100, 1000, 1400, 40000, 1 << 20)] == \
+        ["time-parallel", "time-parallel", "latency", "latency", "wide"]
+    assert ocd.kernel_form(ocd.PlannerParams(H=50), 100) == "latency"      # no time-parallel form above 16 steps
     assert ocd.kernel_form(ocd.PlannerParams(H=50, C=6), 65536) == "wide"
     assert ocd.kernel_form(ocd.PlannerParams(H=15), 1000, episode=True) == "throughput"     # segmented episodes: one form
     assert ocd.kernel_form(ocd.PlannerParams(math_mode=ocd.MATH_PRECISE), 100) == "throughput"
@@ -249,7 +252,8 @@ def test_kernel_form_selection(monkeypatch):
         monkeypatch.setenv("OCD_KERNEL_FORM", form)
         assert ocd.kernel_form(fh, 4096) == want
     monkeypatch.setenv("OCD_KERNEL_FORM", "tp")
-    assert ocd.kernel_form(ocd.PlannerParams(H=15), 4096) == "latency"   # no time-parallel form above H = 8: falls back
+    assert ocd.kernel_form(ocd.PlannerParams(H=15), 4096) == "time-parallel"   # 16 lanes per start up to H = 16
+    assert ocd.kernel_form(ocd.PlannerParams(H=50), 4096) == "latency"   # no time-parallel form above H = 16: falls back
     with pytest.raises(ValueError):
         ocd.kernel_form(ocd.PlannerParams(H=65), 10)
 
@@ -393,3 +397,37 @@ def test_plan_rank_cpus_follows_the_gpu_numa_nodes():
     # a rank with unknown topology sends everyone to the contiguous rule (no core handed out twice)
     plan4 = parallel.plan_rank_cpus(allowed, 4, [list(range(32)), None, list(range(32, 64)), list(range(32, 64))])
     assert sorted(c for p in plan4 for c in p) == allowed
+
+
+def test_cioc_augmented_loss_matches_a_direct_evaluation():
+    """LocalCIOC's host part (second_order_ioc.py:149-165 of the reference): the loss assembled from per-feature gradient
+    rows and Hessian rows equals a direct numpy evaluation, and its autograd gradient in (weights, theta_r) equals
+    central differences."""
+    import torch
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design.second_order_ioc import LocalCIOC
+    rng = np.random.default_rng(3)
+    K, n = 4, 6
+    G = rng.normal(size=(K, n))
+    Hm = rng.normal(size=(K, n, n))
+    w = rng.normal(size=K)
+    th, mu, lm = 0.7, 10.0, 0.3
+
+    def direct(w, th):
+        g = (w[:, None] * G).sum(0)
+        A = (w[:, None, None] * Hm).sum(0) - th * np.eye(n)
+        s, la = np.linalg.slogdet(-A)
+        return -(0.5 * g @ np.linalg.solve(A, g) + 0.5 * s * la - 0.5 * mu * th ** 2 + lm * th), s
+
+    wt = torch.tensor(w, requires_grad=True)
+    tt = torch.tensor(th, dtype=torch.float64, requires_grad=True)
+    loss, sign = LocalCIOC.augmented_loss(wt, tt, torch.as_tensor(G), torch.as_tensor(Hm), mu, lm)
+    ref, s = direct(w, th)
+    assert abs(float(loss) - ref) < 1e-10 and float(sign) == s
+    loss.backward()
+    h = 1e-6
+    for i in range(K):
+        e = np.zeros(K); e[i] = h
+        fd = (direct(w + e, th)[0] - direct(w - e, th)[0]) / (2 * h)
+        assert abs(float(wt.grad[i]) - fd) < 1e-5 * max(1.0, abs(fd))
+    fd = (direct(w, th + h)[0] - direct(w, th - h)[0]) / (2 * h)
+    assert abs(float(tt.grad) - fd) < 1e-5 * max(1.0, abs(fd))
