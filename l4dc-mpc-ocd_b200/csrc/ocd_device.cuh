@@ -906,8 +906,12 @@ __device__ __forceinline__ float solve_start_q(const KParams &k, const GradW &w,
     float sn0, cs0;
     Mth<false>::sincos_(th0, sn0, cs0);
 #pragma unroll 1
-    for (int it = 0; it < k.n_iter; ++it)
+    for (int it = 0; it < k.n_iter; ++it) {
+#if defined(OCD_Q_SYNC) && OCD_Q_SYNC
+        __syncthreads();        // keep the block's warps on the same stretch of the unrolled sweep (instruction fetch)
+#endif
         sgd_iteration_q<HT, NOT_, LT, LAT, LIN>(k, w, x0, y0, v0, th0, sn0, cs0, oth, P, u, q, q2);
+    }
     return -rollout_reward<HT, LT, false, Traj<HT>, LIN>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
 }
 

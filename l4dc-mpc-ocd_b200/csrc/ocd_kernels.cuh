@@ -75,8 +75,16 @@ namespace ocd {
 #ifndef OCD_WIDE_REGS1
 #define OCD_WIDE_REGS1 128      // wide form, one other car (tuning knob)
 #endif
+// Q kernels: problems per block (tuning knob; larger blocks with a barrier per iteration keep an SM's warps on the
+// same stretch of the unrolled sweep) -- OCD_Q_P problems x 3 starts; other start counts keep 32
+#ifndef OCD_Q_P
+#define OCD_Q_P 32
+#endif
+#ifndef OCD_Q_SYNC
+#define OCD_Q_SYNC 0
+#endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
-    __launch_bounds__(kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
+    __launch_bounds__((OCD_IS_Q(HT, NOT_) && 3 * OCD_Q_P > kMaxThreads) ? 3 * OCD_Q_P : kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
     __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? OCD_WIDE_REGS1 : 168) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
@@ -283,9 +291,9 @@ template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
 __global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
-    constexpr int P = kP;     // compile-time, so every slab access is base + immediate
     constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT, NOT_);   // runtime or long horizon: segmented adjoint, controls in shared memory
     constexpr bool QK = OCD_IS_Q(HT, NOT_) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
+    constexpr int P = QK ? OCD_Q_P : kP;     // compile-time, so every slab access is base + immediate
     const bool lin = slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO, QK);
     const Smem m = carve(smem_raw, k, P, false, SEGK, lin, QK);
     const int p = threadIdx.x % P, s = threadIdx.x / P;
@@ -784,7 +792,9 @@ inline int choose_form(const KParams &k, long long B, bool episode) {
 template <int HT, int NOT_, int LT, bool PRECISE>
 int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     constexpr bool SEGK = HT == 0 || OCD_IS_SEGC(HT, NOT_);
-    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, a.P, false, SEGK,
+    const int P = (OCD_IS_Q(HT, NOT_) && !PRECISE) ? OCD_Q_P : a.P;
+    if (P != a.P && k.S != 3) return OCD_EUNSUP;       // tuning builds only
+    const size_t bytes = smem_floats(k.H, k.NO, k.K, k.S, P, false, SEGK,
                                      slab_is_linear(SEGK, PRECISE, k.other_mode, k.H, k.NO, OCD_IS_Q(HT, NOT_) && !PRECISE),
                                      OCD_IS_Q(HT, NOT_) && !PRECISE) * sizeof(float);
     constexpr bool HAS_LAT = HT > 0 && !PRECISE && NOT_ >= 1;
@@ -803,8 +813,8 @@ int launch_solve_t(const KParams &k, const SolveArgs &a, cudaStream_t st) {
     if (form == 2) kern = k_solve<HT, NOT_, LT, PRECISE, ANY_LAT ? 2 : 0>;
     int rc = prepare_smem(kern, bytes);
     if (rc) return rc;
-    const unsigned grid = (unsigned)((a.B + a.P - 1) / a.P);
-    kern<<<grid, k.S * a.P, bytes, st>>>(k, a);
+    const unsigned grid = (unsigned)((a.B + P - 1) / P);
+    kern<<<grid, k.S * P, bytes, st>>>(k, a);
     return cuda_status();
 }
 
