@@ -785,6 +785,13 @@ inline int choose_form(const KParams &k, long long B, bool episode) {
     constexpr bool REGRES = HT > 0 && !OCD_IS_Q(HT, NOT_) && !OCD_IS_SEGC(HT, NOT_);  // register-resident (short) horizons
     // time-parallel: episodes up to 8 steps of horizon (the instantiated episode kernels), solves up to 16
     if (HAS_LAT && HT <= (episode ? kTG : kTGMax) && tiny_batch(B, k.S, tp_problems(HT > 0 ? HT : 1))) return 3;
+    if constexpr (OCD_IS_SEGC(HT, NOT_) && !PRECISE) {
+        // constant-segment-count kernels: the wide form (152 / 168 registers) is at least as fast as the latency form
+        // (255) from ~10^4 problems on, and 30-35 % faster at 16-32 thousand problems with two or more other cars,
+        // where the general rule below would still pick the latency form (profiles/tuning/r02_form_sweep3.log)
+        const int f = forced_form();
+        if (!episode && (f == kFormAuto || f == kFormTp)) return batch_warps(B, kP, k.S) <= 768 ? 1 : 2;
+    }
     if (episode) return pick_form(B, kP, k.S, HAS_LAT, HAS_LAT && NOT_ == 1, NOT_ == 1, true);
     return pick_form(B, kP, k.S, HAS_LAT || SEG_LAT, HAS_LAT || SEG_LAT, REGRES && NOT_ == 1, false, REGRES && NOT_ >= 3);
 }
