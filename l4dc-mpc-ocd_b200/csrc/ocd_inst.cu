@@ -15,3 +15,9 @@ template int launch_episode_t<OCD_HT, OCD_NO, OCD_LT, (OCD_PRECISE != 0)>(const 
                                                                   const EpisodeArgs &, cudaStream_t);
 #endif
 }  // namespace ocd
+
+#ifdef OCD_BLOCK_TIMES   // tuning builds only (scripts/tuning/block_times.py): read back the per-block timestamps
+extern "C" int ocd_debug_block_times(void *host_buf) {
+    return cudaMemcpyFromSymbol(host_buf, ocd::g_block_times, sizeof(ocd::g_block_times)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -287,10 +287,17 @@ __device__ __forceinline__ void predict_other(const KParams &k, float x, float y
 // ---------------------------------------------------------------------------------------------
 // LAT != 0: the straight-line forward sweep (see sgd_iteration): 1 the latency form launched for small batches,
 // 2 the wide form (same code, 128 registers) launched for large batches of the one-other-car shapes.
+#ifdef OCD_BLOCK_TIMES
+__device__ unsigned long long g_block_times[3 * 4096];      // tuning: (start ns, end ns, SM id) of the first 4096 blocks
+#endif
 template <int HT, int NOT_, int LT, bool PRECISE, int LAT = 0>
 __global__ void OCD_KERNEL_BOUNDS(HT, NOT_, LAT)
 k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
+#ifdef OCD_BLOCK_TIMES
+    unsigned long long t_start = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
     constexpr bool SEGK = (HT == 0) || OCD_IS_SEGC(HT, NOT_);   // runtime or long horizon: segmented adjoint, controls in shared memory
     constexpr bool QK = OCD_IS_Q(HT, NOT_) && !PRECISE;   // medium horizon: (d, gx, hy, ke) of every step through shared memory
     constexpr int P = QK ? OCD_Q_P : kP;     // compile-time, so every slab access is base + immediate
@@ -330,6 +337,11 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
     const float x0 = wsrc[0], y0 = wsrc[wstr], v0 = wsrc[2 * wstr], th0 = wsrc[3 * wstr];
     const GradW gw = make_gradw<LT>(k, m.wraw + p, P);
     const float speed = a.cur_speed ? a.cur_speed[b] : v0;
+#ifdef OCD_STAGGER_NS
+    // tuning: start the warps of an SM out of phase (a kernel of a few waves otherwise runs its warps in lock step:
+    // every warp in the MUFU-heavy stretch of the sweep at the same time)
+    if (!PRECISE && LAT == 2) __nanosleep(((blockIdx.x * 3u + (unsigned)s) % OCD_STAGGER_MOD) * OCD_STAGGER_NS);
+#endif
     const int H = HT > 0 ? HT : k.H;
     Traj<(SEGK ? 1 : HT)> u;                         // register-resident controls (short and medium compile-time horizons)
     const SmemTraj us{SEGK ? m.useg + (size_t)threadIdx.x * seg_u_stride(k.H) : nullptr};   // shared-memory controls
@@ -382,6 +394,17 @@ k_solve(const __grid_constant__ KParams k, const SolveArgs a) {
             a.plan[(size_t)(t * 2 + 1) * B + b] = SEGK ? us.ang(t) : u.ang(SEGK ? 0 : t);
         }
     }
+#ifdef OCD_BLOCK_TIMES
+    if (threadIdx.x == 0 && blockIdx.x < 4096) {
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_block_times[3 * blockIdx.x] = t_start;
+        g_block_times[3 * blockIdx.x + 1] = t_end;
+        g_block_times[3 * blockIdx.x + 2] = smid;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
