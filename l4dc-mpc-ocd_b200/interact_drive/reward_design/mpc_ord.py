@@ -13,6 +13,8 @@ import sys
 import time
 from typing import Optional, Sequence
 
+import math
+
 import numpy as np
 import scipy.stats
 
@@ -168,6 +170,7 @@ class MPC_ORD:
         self.program = compile_world(world, car)
         self.kernel_launches = 0
         self._dev_cache = {}
+        self._batch_cache = None
 
     # -- the batched core ------------------------------------------------------------------------------
     @staticmethod
@@ -178,19 +181,29 @@ class MPC_ORD:
         if w.ndim == 2:
             w = w[0]
         for _ in range(3):
-            w = w / np.linalg.norm(w)
+            w = w / math.sqrt(float(w.dot(w)))       # np.linalg.norm of a real vector: sqrt(x.dot(x)), without the call overhead
         return w.astype(np.float32)
 
     def _episode_batch(self, weight_matrix, inits: Optional[Sequence] = None) -> dict:
         """The flat episode batch of `weight_matrix` [n_cand, K] (raw candidates) x inits [n_init, 4] x num_samples:
         planning weights W [nc, K], robot states [nc*ni*ns, 4], the candidate of every episode and -- replanning world --
-        the car that vanishes in it.  Advances the world's own reset toggle like the serial loops would."""
-        W = np.stack([self._planning_weights(w) for w in np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))])
+        the car that vanishes in it.  Advances the world's own reset toggle like the serial loops would.  Everything
+        that depends only on the initial states and the candidate count is kept from one call to the next (the CMA-ES
+        loop calls this once per generation with the same states)."""
+        Wm = np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))
+        W = np.stack([self._planning_weights(w) for w in Wm])
         inits = self.init_car_states if inits is None else inits
-        I = np.stack([as_f32(s, (4,)) for s in inits])
-        nc, ni, ns = W.shape[0], I.shape[0], self.num_samples
-        robot = np.repeat(np.tile(I, (nc, 1)), ns, axis=0)                       # [nc*ni*ns, 4]
-        widx = np.repeat(np.arange(nc, dtype=np.int32), ni * ns)
+        src = np.asarray(inits, dtype=np.float64)
+        nc, ns = W.shape[0], self.num_samples
+        c = self._batch_cache
+        if c is None or c["nc"] != nc or c["ns"] != ns or c["src"].shape != src.shape or not np.array_equal(c["src"], src):
+            I = np.stack([as_f32(s, (4,)) for s in inits])
+            ni = I.shape[0]
+            c = dict(nc=nc, ns=ns, src=src.copy(), I=I, robot=np.repeat(np.tile(I, (nc, 1)), ns, axis=0),   # [nc*ni*ns, 4]
+                     widx=np.repeat(np.arange(nc, dtype=np.int32), ni * ns))
+            self._batch_cache = c
+        I, robot, widx = c["I"], c["robot"], c["widx"]
+        ni = I.shape[0]
         unlucky = None
         if self.program.replanning:
             # the reference resets the world once per (candidate, init, sample), serially, and every reset toggles the
