@@ -72,6 +72,9 @@ namespace ocd {
 #ifndef OCD_SEGC_SEG
 #define OCD_SEGC_SEG 5      // steps per segment of the long compile-time horizons (checkpoint rows are sized for 5)
 #endif
+#ifndef OCD_WIDE_REGS_MANY
+#define OCD_WIDE_REGS_MANY 168  // wide form, other car counts (tuning knob)
+#endif
 #ifndef OCD_WIDE_REGS1
 #define OCD_WIDE_REGS1 128      // wide form, one other car (tuning knob)
 #endif
@@ -85,7 +88,7 @@ namespace ocd {
 #endif
 #define OCD_KERNEL_BOUNDS(HT, NOT_, LAT)                                  \
     __launch_bounds__((OCD_IS_Q(HT, NOT_) && 3 * OCD_Q_P > kMaxThreads) ? 3 * OCD_Q_P : kMaxThreads, ((LAT) != 0 || (HT) > 0) ? 1 : 3)      \
-    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? OCD_WIDE_REGS1 : 168) : ((HT) > 0 ? 72 : 96))))
+    __maxnreg__((LAT) == 1 ? 255 : (OCD_IS_Q(HT, NOT_) ? OCD_Q_REGS(NOT_) : OCD_IS_SEGC(HT, NOT_) ? OCD_SEGC_REGS_(NOT_) : ((LAT) == 2 ? (((NOT_) == 1 || ((HT) > 0 && (NOT_) == 3)) ? OCD_WIDE_REGS1 : OCD_WIDE_REGS_MANY) : ((HT) > 0 ? 72 : 96))))
 static constexpr int kP = 32;             // problems per block: one warp per start
 static constexpr int kMaxThreads = 6 * kP; // S=6 starts
 
