@@ -541,7 +541,7 @@ __device__ __forceinline__ void feature_grad(const KParams &k, const GradW &w, f
             }
             const float rr = fmaf(r1, r1, r2 * r2);
             const float T = Mth<false>::rcp_(1.0f + Mth<false>::ex2_(r1 - r2));
-            const float dT = (T * (1.0f - T)) * (k.fl_c * rr);
+            const float dT = fmaf(-T, T, T) * (k.fl_c * rr);          // T (1 - T) as one FMA
             gx = fmaf(w.wfence, copysignf(fmaf(dT, ax, T), x), gx);
         }
     }
