@@ -558,7 +558,8 @@ def test_kernel_forms_agree(engine, monkeypatch):
                                     (2, (-0.1, 0.0, 0.1), 1.0, 6, False), (2, (-0.1, 0.0, 0.1), 1.0, 5, True),
                                     (4, (-0.1, 0.0, 0.1), 1.0, 5, False), (6, (-0.1, 0.0, 0.1), 1.0, 5, False),
                                     (2, (-0.1, 0.0, 0.1), 1.0, 15, False), (5, (-0.1, 0.0, 0.1), 1.0, 12, False),
-                                    (3, (-0.1, 0.0, 0.1), 1.0, 15, False), (2, (-0.1, 0.0, 0.1), 1.0, 50, False)):
+                                    (3, (-0.1, 0.0, 0.1), 1.0, 15, False), (2, (-0.1, 0.0, 0.1), 1.0, 50, False),
+                                    (2, (-0.1, 0.0, 0.1), 1.0, 15, True), (6, (-0.1, 0.0, 0.1), 1.0, 15, False)):
         B, n = (32768 if (extra or H == 50) else 65536), 3000
         batch = synthetic.make_batch(B, C=C, lane_x=lane_x, seed=321)
         p = ocd.PlannerParams(H=H, C=C, lane_x=lane_x, num_lanes=len(lane_x), target_speed=ts, extra_inits=extra,
