@@ -282,6 +282,7 @@ def test_reward_heatmap_matches_oracle_features():
 
 
 def test_generalization_evaluation_is_one_launch():
+    import oracle as O
     from l4dc_mpc_ocd_b200.experiments import generalization_data as gd
     env = run_mpc_ord.envs["local_opt"]
     weights = {(1, 2): env["tuned_weights"], (3, 2): np.array([-5, 0., 0., -10, 0, -50, -50])}
@@ -292,6 +293,16 @@ def test_generalization_evaluation_is_one_launch():
     m = MPC_ORD(world, car, [], env["eval_horizon"], num_samples=env["num_eval_samples"], verbose=False)
     one = m.eval_weights_for_init(test_inits[2], np.asarray(weights[(1, 2)], np.float64), False)
     assert abs(one - res[2][(1, 2)]) <= 1e-6 * abs(one)
+    # ... and every (weights, held-out state) return against the ORACLE's serial episodes (1e-3 relative, BASELINE)
+    spec = O.scenario_params("local_opt")
+    T, ns = env["eval_horizon"], env["num_eval_samples"]
+    w_true = np.asarray(m.designer_weights, np.float32)
+    for key, wv in weights.items():
+        wp = MPC_ORD._planning_weights(np.asarray(wv, np.float64))
+        ri = np.repeat(np.asarray(test_inits[:4], np.float32), ns, axis=0)
+        ref = O.episode_batch(spec.params, spec.scenario, ri, np.tile(wp, (ri.shape[0], 1)), w_true, T).reshape(4, ns).sum(1)
+        got = np.array([res[i][key] for i in range(4)])
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)) <= 1e-3, (key, got, ref)
     hist = [(np.ones(7), -3.0), (np.arange(7.0), -1.0), (np.zeros(7), -2.0)]
     np.testing.assert_array_equal(gd.best_weights(hist), np.arange(7.0))
     np.testing.assert_array_equal(gd.best_weights(hist, num_evals=1), np.ones(7))
