@@ -947,28 +947,35 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 #pragma unroll 1
     for (int it = 0; it < k.n_iter; ++it) {
         float A[HT], W[HT], sv[HT + 1], sc[HT + 1], ss[HT + 1], sd[HT];    // [j]: at the state before step j
+        {   // the lanes exchange the CLIPPED controls (the rollout uses nothing else; the raw ones only mask the update)
+            const float ac_own = fmaxf(fminf(ua, 4.0f), -8.0f);
+            const float oc_own = fmaxf(fminf(uw, 4.0f), -4.0f);
 #pragma unroll
-        for (int j = 0; j < HT; ++j) {
-            A[j] = __shfl_sync(OCD_FULL, ua, j, TG);
-            W[j] = __shfl_sync(OCD_FULL, uw, j, TG);
+            for (int j = 0; j < HT; ++j) {
+                A[j] = __shfl_sync(OCD_FULL, ac_own, j, TG);
+                W[j] = __shfl_sync(OCD_FULL, oc_own, j, TG);
+            }
         }
-        float x = x0, y = y0, v = v0, th = th0, sn = sn0, cs = cs0;
-        float mx_ = 0.0f, my_ = 0.0f, mv_ = 0.0f, msn = 0.0f, mcs = 0.0f;
+        float v = v0, th = th0, sn = sn0, cs = cs0;
+        // this lane's own state (after step tt) freezes once its step has passed: the position is accumulated under the
+        // predicate j <= tt (same FMAs in the same order as the other kernels' rollout, no selects)
+        float mx_ = x0, my_ = y0, mv_ = v0, msn = sn0, mcs = cs0;
 #pragma unroll
         for (int j = 0; j < HT; ++j) {
-            const float ac = fmaxf(fminf(A[j], 4.0f), -8.0f);
-            const float oc = fmaxf(fminf(W[j], 4.0f), -4.0f);
-            const float total = fmaf(-k.mu, v * v, ac);
+            const float total = fmaf(-k.mu, v * v, A[j]);
             const float dist = fmaf(total, k.hdt2, v * k.dt);
             sv[j] = v; sc[j] = cs; ss[j] = sn; sd[j] = dist;
-            x = fmaf(cs, dist, x);
-            y = fmaf(sn, dist, y);
+            const bool upto = j <= tt;
+            if (upto) {
+                mx_ = fmaf(cs, dist, mx_);
+                my_ = fmaf(sn, dist, my_);
+            }
             v = fmaf(total, k.dt, v);
-            th = fmaf(oc, k.dt, th);
+            th = fmaf(W[j], k.dt, th);
             Mth<false>::sincos_(th, sn, cs);
-            const bool mine = j == tt;
-            mx_ = mine ? x : mx_; my_ = mine ? y : my_; mv_ = mine ? v : mv_;
-            msn = mine ? sn : msn; mcs = mine ? cs : mcs;
+            if (upto) {
+                mv_ = v; msn = sn; mcs = cs;
+            }
         }
         sv[HT] = v; sc[HT] = cs; ss[HT] = sn;
         float gx, hy, ke, unused;
