@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 import l4dc_mpc_ocd_b200 as ocd                  # noqa: E402
 from l4dc_mpc_ocd_b200 import synthetic         # noqa: E402
 
-LR = {5: 0.1, 15: 0.03, 50: 0.003}
+LR = {5: 0.1, 15: 0.02, 50: 0.0003}
 
 
 def main():
