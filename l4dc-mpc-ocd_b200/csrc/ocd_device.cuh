@@ -1022,7 +1022,39 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
         u.ua[j] = __shfl_sync(OCD_FULL, ua, j, TG);
         u.uw[j] = __shfl_sync(OCD_FULL, uw, j, TG);
     }
-    return -rollout_reward<HT, LT, false, Traj<HT>>(k, wraw, ws, x0, y0, v0, th0, oth, P, u);
+    // Final loss -R(u), R = sum_t w . phi(s_{t+1}) accumulated in step order (rollout_reward, naive_planner.py:43-77).
+    // Every lane evaluates the reward of ITS step only: it reaches that state with rollout_reward's own dynamics
+    // (dynamics_step's FMAs, the position accumulated under j <= tt), the lane values are all-gathered and added in
+    // step order -- the same additions in the same order, but one feature evaluation on the dependent chain, not HT.
+    {
+        const float ac_own = fmaxf(fminf(ua, 4.0f), -8.0f);
+        const float oc_own = fmaxf(fminf(uw, 4.0f), -4.0f);
+        float v = v0, th = th0, sn = sn0, cs = cs0;
+        float xq = x0, yq = y0, vq = v0, snq = sn0;
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            const float aj = __shfl_sync(OCD_FULL, ac_own, j, TG);
+            const float wj = __shfl_sync(OCD_FULL, oc_own, j, TG);
+            const float total = fmaf(-k.mu, v * v, aj);
+            const float dist = fmaf(total, k.hdt2, v * k.dt);
+            const bool upto = j <= tt;
+            if (upto) {
+                xq = fmaf(cs, dist, xq);
+                yq = fmaf(sn, dist, yq);
+            }
+            v = fmaf(total, k.dt, v);
+            th = fmaf(wj, k.dt, th);
+            Mth<false>::sincos_(th, sn, cs);
+            if (upto) {
+                vq = v; snq = sn;
+            }
+        }
+        const float rv = reward_value<LT, false, true, false>(k, wraw, ws, xq, yq, vq, snq, omine, 2 * P, P);
+        float r = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HT; ++j) r = __fadd_rn(r, __shfl_sync(OCD_FULL, rv, j, TG));
+        return -r;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
