@@ -997,18 +997,39 @@ __device__ __forceinline__ float solve_start_tp(const KParams &k, const GradW &w
 #pragma unroll
         for (int jj = 0; jj < HT; ++jj) {
             const int j = HT - 1 - jj;
-            // the gradient at s_{j+1} plus the adjoint, fused exactly as the single-thread kernels fuse them
-            const float mx = GX[j] + lx;
-            const float my = fmaf(w.wcy, HY[j], ly);
-            const float mv = fmaf(KE[j], ss[j + 1], lv);
-            const float mth = fmaf(__fmul_rn(KE[j], sv[j + 1]), sc[j + 1], lth);
-            const float ld = fmaf(sc[j], mx, ss[j] * my);
-            lv = fmaf(fmaf(c1, sv[j], 1.0f), mv, fmaf(c2, sv[j], k.dt) * ld);
-            lth = fmaf(sd[j], fmaf(sc[j], my, -(ss[j] * mx)), mth);
-            lx = mx;
-            ly = my;
-            const bool mine = j == tt;
-            ld_ = mine ? ld : ld_; mv_t = mine ? mv : mv_t; mth_t = mine ? mth : mth_t;
+            // the gradient at s_{j+1} plus the adjoint, fused exactly as the single-thread kernels fuse them.  A lane
+            // walks the chain down to its own step and stops there (the steps below it run under a false predicate), so
+            // what the three terms hold after the loop are the values of its own step -- no select chain
+            // In C (what every other kernel's reverse sweep writes, statement for statement):
+            //   if (j >= tt) { mx = GX[j] + lx;  my = fmaf(wcy, HY[j], ly);  mv = fmaf(KE[j], ss[j+1], lv);
+            //                  mth = fmaf(KE[j] * sv[j+1], sc[j+1], lth);  ld = fmaf(sc[j], mx, ss[j] * my);
+            //                  lv = fmaf(fmaf(c1, sv[j], 1), mv, fmaf(c2, sv[j], dt) * ld);
+            //                  lth = fmaf(sd[j], fmaf(sc[j], my, -(ss[j] * mx)), mth);  lx = mx;  ly = my; }
+            // written as predicated PTX because ptxas turns the C form into a divergent branch per step (BSSY / BRA /
+            // BSYNC); explicit .rn on every mul / add keeps ptxas from contracting them, so the roundings are the C form's.
+            asm("{\n\t"
+                ".reg .pred p;\n\t"
+                ".reg .f32 t0, t1, t2, t3, t4, t5;\n\t"        // temporaries are written unconditionally (no old value to keep)
+                "setp.ne.s32 p, %21, 0;\n\t"
+                "@p add.rn.f32 %0, %7, %0;\n\t"               // lx := mx = GX + lx
+                "@p fma.rn.f32 %1, %17, %8, %1;\n\t"          // ly := my = wcy HY + ly
+                "@p fma.rn.f32 %5, %9, %10, %2;\n\t"          // mv = KE ss[j+1] + lv
+                "mul.rn.f32 t0, %9, %11;\n\t"                 // KE sv[j+1]
+                "@p fma.rn.f32 %6, t0, %12, %3;\n\t"          // mth = (KE sv[j+1]) sc[j+1] + lth
+                "mul.rn.f32 t1, %14, %1;\n\t"                 // ss[j] my
+                "@p fma.rn.f32 %4, %13, %0, t1;\n\t"          // ld = sc[j] mx + ss[j] my
+                "fma.rn.f32 t2, %18, %16, 0f3F800000;\n\t"    // c1 sv[j] + 1
+                "fma.rn.f32 t3, %19, %16, %20;\n\t"           // c2 sv[j] + dt
+                "mul.rn.f32 t3, t3, %4;\n\t"                  // (c2 sv[j] + dt) ld
+                "@p fma.rn.f32 %2, t2, %5, t3;\n\t"           // lv
+                "mul.rn.f32 t4, %14, %0;\n\t"                 // ss[j] mx
+                "neg.f32 t4, t4;\n\t"
+                "fma.rn.f32 t5, %13, %1, t4;\n\t"             // sc[j] my - ss[j] mx
+                "@p fma.rn.f32 %3, %15, t5, %6;\n\t"          // lth = sd[j] (...) + mth
+                "}"
+                : "+f"(lx), "+f"(ly), "+f"(lv), "+f"(lth), "+f"(ld_), "+f"(mv_t), "+f"(mth_t)
+                : "f"(GX[j]), "f"(HY[j]), "f"(KE[j]), "f"(ss[j + 1]), "f"(sv[j + 1]), "f"(sc[j + 1]), "f"(sc[j]),
+                  "f"(ss[j]), "f"(sd[j]), "f"(sv[j]), "f"(w.wcy), "f"(c1), "f"(c2), "f"(k.dt), "r"((int)(j >= tt)));
         }
         // every lane walks the whole adjoint chain, but updates only its own control (same formula, same operands as
         // the single-thread kernels' update of step tt)
