@@ -759,7 +759,7 @@ inline int prepare_smem(KernelT kern, size_t bytes) {
 
 // Which form runs (measured on B200, scripts/tuning/form_sweep*.py, form_ep.py, wide_regs.sh; times in
 // DESIGN.md):
-//  * time-parallel: up to ~800 warps of 4 starts (about 1 000 problems) -- below that its shorter dependent chain
+//  * time-parallel: up to 888 warps of 4 starts (two of its three-warp blocks per SM: 1 184 problems) -- below that its shorter dependent chain
 //    wins, above it its 4x instruction count per solve loses;
 //  * latency form: up to 2 048 warps (one other car: one wave of its four blocks per SM) or 4 096 warps;
 //  * beyond that the WIDE form -- the same straight-line code under a register cap -- wherever it beats the
@@ -783,9 +783,10 @@ inline int forced_form() {
 inline long long batch_warps(long long B, int P, int S) { return ((B + P - 1) / P) * S; }
 inline bool tiny_batch(long long B, int S, int P = kTP) {      // P: problems per warp of the time-parallel form
     const int f = forced_form();
-    // 8 lanes per start: up to ~800 warps; 16 lanes (H = 9..16) up to ~1 800: H = 15, 720 problems 0.146 ms against
+    // 8 lanes per start: up to two three-warp blocks per SM, 888 warps (1 080 finite_horizon episodes 0.515 ms against 0.599 for
+    // the latency form, 1 620 episodes 0.716 against 0.599: profiles/tuning/r02_tp_cross.log); 16 lanes (H = 9..16) up to ~1 800: H = 15, 720 problems 0.146 ms against
     // 0.207 ms for the latency form, 1 440 problems 0.191 against 0.186 (profiles/tuning/r02_tp16.log)
-    return f ? f == kFormTp : batch_warps(B, P, S) <= (P == kTP ? 800 : 1800);
+    return f ? f == kFormTp : batch_warps(B, P, S) <= (P == kTP ? 888 : 1800);
 }
 // -> 0 throughput, 1 latency, 2 wide.
 inline int pick_form(long long B, int P, int S, bool has_lat, bool has_wide, bool one_other, bool episode,

@@ -230,7 +230,7 @@ def test_kernel_form_selection(monkeypatch):
     import l4dc_mpc_ocd_b200 as ocd
     monkeypatch.delenv("OCD_KERNEL_FORM", raising=False)
     fh = ocd.PlannerParams()                                            # H=5, one other car: the bench shape
-    assert [ocd.kernel_form(fh, B) for B in (1, 45, 1000, 1100, 20000, 30000, 1 << 20)] == \
+    assert [ocd.kernel_form(fh, B) for B in (1, 45, 1100, 1200, 20000, 30000, 1 << 20)] == \
         ["time-parallel", "time-parallel", "time-parallel", "latency", "latency", "wide", "wide"]
     assert [ocd.kernel_form(fh, B, episode=True) for B in (45, 5000, 60000, 100000)] == \
         ["time-parallel", "latency", "wide", "throughput"]
