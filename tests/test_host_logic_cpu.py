@@ -431,3 +431,16 @@ def test_cioc_augmented_loss_matches_a_direct_evaluation():
         assert abs(float(wt.grad[i]) - fd) < 1e-5 * max(1.0, abs(fd))
     fd = (direct(w, th + h)[0] - direct(w, th - h)[0]) / (2 * h)
     assert abs(float(tt.grad) - fd) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_packaging_metadata_lists_every_subpackage():
+    """pyproject.toml maps the importable name onto `l4dc-mpc-ocd_b200/`; its package list must name every directory
+    with an __init__.py there, or an installed copy would miss modules the in-tree alias finds."""
+    import tomllib
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    meta = tomllib.loads((root / "pyproject.toml").read_text())["tool"]["setuptools"]
+    src = root / meta["package-dir"]["l4dc_mpc_ocd_b200"]
+    found = {"l4dc_mpc_ocd_b200" + "".join("." + p for p in d.parent.relative_to(src).parts)
+             for d in src.rglob("__init__.py") if "csrc" not in d.parts}
+    assert set(meta["packages"]) == found
