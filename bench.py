@@ -15,7 +15,8 @@ dependent-free FMA kernel, since MEASURED_PEAKS.json has no FP32 figure), hbm (a
 vs the measured copy bandwidth, to show the path is nowhere near memory-bound), e2e (same metric
 through the host-buffer C ABI, copies inside), cpu_baseline (the CPU oracle on this box's cores),
 cmaes (candidate-evals/s of one CMA-ES generation of BASELINE configs[1..3]: finite_horizon n_inits 5, local_opt
-n_inits 10, replanning T=20 x 2 samples -- one episode launch each), cmaes_multi (64 independent CMA-ES runs per GPU in
+n_inits 10, replanning T=20 x 2 samples -- one episode launch each), cmaes_dropin (the first of them through the
+MPC_ORD drop-in, host wall clock), cmaes_multi (64 independent CMA-ES runs per GPU in
 lock step: the axis on which candidate-evals/s scales with GPUs), horizons (solves/s at H = 15 and H = 50, the other
 horizons BASELINE's metric names), sweep (corner points of BASELINE configs[4]), e2e_first_control (the
 receding-horizon caller's host call: only plan[0] comes back), cpu_baseline_serial (the reference's own driving style:
@@ -383,6 +384,8 @@ def main():
         line["cmaes_configs"] = [line["cmaes"],
                                  cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "local_opt", 10),
                                  cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "replanning", 5)]
+        if world_size == 1:
+            line["cmaes_dropin"] = cmaes_dropin_leg()
         # independent CMA-ES runs in lock step: 64 runs per GPU (weak), and a fixed 512 runs over all GPUs (strong)
         line["cmaes_multi"] = cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "finite_horizon", 5,
                                         runs=64 * world_size)
@@ -471,6 +474,35 @@ def sweep_leg(eng, ocd, synthetic, rank, world_size, max_over_ranks, barrier, no
                              "solves_per_sec": B * world_size / (ms * 1e-3), "form": ocd.kernel_form(p, B),
                              "frac_of_nominal_fp32": round(fl * B / (ms * 1e-3) / nominal, 4), "finite": finite})
     return rows
+
+
+def cmaes_dropin_leg():
+    """The same generation of BASELINE configs[1] end to end through the reference-facing drop-in: numpy candidates into
+    `MPC_ORD.eval_weights_batch`, numpy returns out (host wall clock around the call: struct packing, the copy-in /
+    kernel / copy-out graph of `ocd_episode_batch_host`, the synchronisation), and a short `optimize_cmaes` run with
+    the CMA-ES bookkeeping between the generations."""
+    import torch
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env
+    car, world, inits = finite_horizon_env(horizon=5, env_seeds=[1, 2, 3, 4, 5], debug=False)
+    ord_ = MPC_ORD(world, car, inits, designer_horizon=15, verbose=False)
+    rng = np.random.default_rng(0)
+    W = np.asarray(car.weights)[None] + 0.05 * rng.normal(size=(9, 7))
+    for _ in range(5):
+        ord_.eval_weights_batch(W)
+    torch.cuda.synchronize()
+    reps = 50
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ord_.eval_weights_batch(W)
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    gens = 30
+    t0 = time.perf_counter()
+    ord_.optimize_cmaes(seed=1, sigma0=0.05, maxiter=gens)
+    ms_opt = 1e3 * (time.perf_counter() - t0) / gens
+    return {"workload": "finite_horizon cmaes --n_inits 5 through MPC_ORD (numpy in, numpy out): 9 candidates x 5 inits x 15 "
+                        "control steps per generation",
+            "eval_weights_batch_ms": ms, "candidate_evals_per_sec": 9 / (ms * 1e-3),
+            "optimize_cmaes_ms_per_generation": ms_opt, "generations": gens}
 
 
 def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier, scenario, n_inits, runs=1):

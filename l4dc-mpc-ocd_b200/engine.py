@@ -572,7 +572,7 @@ class HostContext:
         ret = np.empty((B,), np.float32)
         fw = np.empty((p.C, 4, B), np.float32) if final_world else None
         ps, ss = structs if structs is not None else (p.c_struct(), sc.c_struct())
-        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        vp = lambda a: None if a is None else a.ctypes.data          # plain address: argtypes make it a void pointer
         rc = N.lib.ocd_episode_batch_host(self._h, C.addressof(ps), C.addressof(ss), vp(ri), vp(oi), vp(w), Bw,
                                           vp(idx), vp(tw), vp(ul), int(t0), int(T), vp(ret), vp(fw), B)
         N.check(rc, "ocd_episode_batch_host")

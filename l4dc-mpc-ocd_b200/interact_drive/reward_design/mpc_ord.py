@@ -191,7 +191,13 @@ class MPC_ORD:
         that depends only on the initial states and the candidate count is kept from one call to the next (the CMA-ES
         loop calls this once per generation with the same states)."""
         Wm = np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))
-        W = np.stack([self._planning_weights(w) for w in Wm])
+        if Wm.ndim == 3:                                     # rows given as [1, K] (the reference passes such weights around)
+            Wm = Wm[:, 0, :]
+        # _planning_weights for every row: the norms row by row (the same dot product the scalar path takes), the three
+        # divisions for all rows at once (elementwise, so the same quotients)
+        for _ in range(3):
+            Wm = Wm / np.array([math.sqrt(float(w.dot(w))) for w in Wm])[:, None]
+        W = Wm.astype(np.float32)
         inits = self.init_car_states if inits is None else inits
         src = np.asarray(inits, dtype=np.float64)
         nc, ns = W.shape[0], self.num_samples
@@ -305,7 +311,7 @@ class MPC_ORD:
         returns ret [nc, ni, ns].  -> -totals."""
         totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
         for w, total in zip(W, totals):
-            wn = w / np.linalg.norm(w)
+            wn = w / math.sqrt(float(w.dot(w)))                  # w / np.linalg.norm(w) (reference :120) without the call overhead
             if self.verbose:
                 print('ITERATION', self.iter)
                 print('eval', wn)
