@@ -16,7 +16,8 @@ vs the measured copy bandwidth, to show the path is nowhere near memory-bound), 
 through the host-buffer C ABI, copies inside), cpu_baseline (the CPU oracle on this box's cores),
 cmaes (candidate-evals/s of one CMA-ES generation of BASELINE configs[1..3]: finite_horizon n_inits 5, local_opt
 n_inits 10, replanning T=20 x 2 samples -- one episode launch each), cmaes_dropin (the first of them through the
-MPC_ORD drop-in, host wall clock), cmaes_multi (64 independent CMA-ES runs per GPU in
+MPC_ORD drop-in, host wall clock), cmaes_multi_dropin (64 lock-step runs through optimize_cmaes_lockstep, host wall
+clock), cmaes_multi (64 independent CMA-ES runs per GPU in
 lock step: the axis on which candidate-evals/s scales with GPUs), horizons (solves/s at H = 15 and H = 50, the other
 horizons BASELINE's metric names), sweep (corner points of BASELINE configs[4]), e2e_first_control (the
 receding-horizon caller's host call: only plan[0] comes back), cpu_baseline_serial (the reference's own driving style:
@@ -386,6 +387,7 @@ def main():
                                  cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "replanning", 5)]
         if world_size == 1:
             line["cmaes_dropin"] = cmaes_dropin_leg()
+            line["cmaes_multi_dropin"] = cmaes_multi_dropin_leg()
         # independent CMA-ES runs in lock step: 64 runs per GPU (weak), and a fixed 512 runs over all GPUs (strong)
         line["cmaes_multi"] = cmaes_leg(eng, ocd, dd, rank, world_size, max_over_ranks, barrier, "finite_horizon", 5,
                                         runs=64 * world_size)
@@ -503,6 +505,31 @@ def cmaes_dropin_leg():
                         "control steps per generation",
             "eval_weights_batch_ms": ms, "candidate_evals_per_sec": 9 / (ms * 1e-3),
             "optimize_cmaes_ms_per_generation": ms_opt, "generations": gens}
+
+
+def cmaes_multi_dropin_leg(runs=64, gens=15):
+    """`cmaes_multi` end to end: `optimize_cmaes_lockstep` over 64 independent finite_horizon runs (n_inits 5 each), host
+    wall clock per generation -- the launch AND the Python side of a generation (CMA-ES updates of all runs as stacked
+    numpy calls, candidate normalisation, per-run histories)."""
+    import torch
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design.mpc_ord import MPC_ORD, finite_horizon_env, optimize_cmaes_lockstep
+
+    def make():
+        out = []
+        for r in range(runs):
+            car, world, inits = finite_horizon_env(horizon=5, env_seeds=[1000 + 5 * r + i for i in range(5)], debug=False)
+            out.append(MPC_ORD(world, car, inits, designer_horizon=15, verbose=False))
+        return out
+    seeds = list(range(1, runs + 1))
+    optimize_cmaes_lockstep(make(), seeds, sigma0=0.05, maxiter=2)              # graph capture, buffers
+    rs = make()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    optimize_cmaes_lockstep(rs, seeds, sigma0=0.05, maxiter=gens)
+    dt = time.perf_counter() - t0
+    return {"workload": f"finite_horizon cmaes --n_inits 5, {runs} independent runs in lock step through "
+                        f"optimize_cmaes_lockstep, {gens} generations (+ the evaluation of the designer weights)",
+            "ms_per_generation": 1e3 * dt / (gens + 1), "candidate_evals_per_sec": runs * (9 * gens + 1) / dt, "runs": runs}
 
 
 def cmaes_leg(eng, ocd, dist, rank, world_size, max_over_ranks, barrier, scenario, n_inits, runs=1):

@@ -49,6 +49,20 @@ def sample_init_state(env_seed, x, y, speed):
     return np.array([_truncnorm_sample(*x), _truncnorm_sample(*y), _truncnorm_sample(*speed), np.pi / 2])
 
 
+def _unit_rows(W: np.ndarray) -> np.ndarray:
+    """w / np.linalg.norm(w) for every row of W [n, K] (float64): np.linalg.norm of a real vector is sqrt(x.dot(x)),
+    and np.vecdot runs that same BLAS dot over each row, so the quotients are the per-row ones bit for bit -- in one
+    call instead of n."""
+    return W / np.sqrt(np.vecdot(W, W))[:, None]
+
+
+def _planning_weight_rows(W: np.ndarray) -> np.ndarray:
+    """MPC_ORD._planning_weights for every row of W [n, K]: three normalisations in float64, then the cast."""
+    for _ in range(3):
+        W = _unit_rows(W)
+    return W.astype(np.float32)
+
+
 def _launch_sharded(eng, ord_, W, robot, widx, unlucky):
     """One process per GPU: this rank runs its contiguous shard of the episodes, then the per-episode rows -- return
     and final world state -- are all-gathered (the path's only exchange step), so every rank holds the same data and
@@ -66,63 +80,128 @@ def _launch_sharded(eng, ord_, W, robot, widx, unlucky):
     return np.ascontiguousarray(rows[:, 0]), rows[-1, 1:].reshape(p.C, 4)
 
 
-def eval_weights_lockstep(runs: Sequence["MPC_ORD"], weight_lists: Sequence[Sequence]) -> list:
+def _run_signature(r: "MPC_ORD") -> tuple:
+    """What two MPC_ORDs must share to be evaluated in one launch (the compiled structs are kept per object)."""
+    sig = getattr(r, "_lockstep_sig", None)
+    if sig is None:
+        sig = r._lockstep_sig = (bytes(r.program.params.c_struct()), bytes(r.program.scenario.c_struct()))
+    return sig + (r.designer_horizon, r.num_samples, as_f32(r.designer_weights).tobytes())
+
+
+def _candidate_rows(wl, K: int) -> np.ndarray:
+    """One run's candidates as a float64 [n, K] array (rows may come as [K] or [1, K], like the reference passes them)."""
+    if isinstance(wl, np.ndarray) and wl.ndim == 2 and wl.shape[1] == K:
+        return np.asarray(wl, dtype=np.float64)
+    if len(wl) == 0:
+        return np.zeros((0, K))
+    rows = [np.asarray(w, dtype=np.float64) for w in wl]
+    return np.stack([w[0] if w.ndim == 2 else w for w in rows])
+
+
+def eval_weights_lockstep(runs: Sequence["MPC_ORD"], weight_lists: Sequence[Sequence],
+                          session: Optional[dict] = None) -> list:
     """`eval_weights_batch` for several independent MPC_ORDs in ONE launch: run r evaluates weight_lists[r] (possibly
     empty) on ITS initial states.  The reference runs such optimisations in separate worker processes
     (`Pool(len(init_states_groups))`, experiments/run_mpc_ord.py:83-90); here their generations share a kernel launch
     -- sharded over the ranks when a process group is up -- and every run's history advances exactly as if it had
-    been evaluated alone (each episode's result does not depend on what else is in the batch).
+    been evaluated alone (each episode's result does not depend on what else is in the batch).  The host side of a
+    generation is vectorised over the runs too -- one normalisation of all candidates, one launch through the host
+    context with the episode layout kept between generations -- because with many runs it, not the launch, is what a
+    generation costs.
+    `session`: a dict the caller keeps across the calls of ONE optimisation (optimize_cmaes_lockstep does): the runs
+    are checked against each other once, and the state a serial evaluation leaves in the Python objects (last weights,
+    last initial state, final world) is parked in it instead of being written after every generation --
+    `finish_lockstep_session` writes it at the end.  Without it every call checks and writes.
     -> list of -totals arrays, one per run."""
     runs = list(runs)
     ref = runs[0]
-    sig = (bytes(ref.program.params.c_struct()), bytes(ref.program.scenario.c_struct()), ref.designer_horizon,
-           ref.num_samples, as_f32(ref.designer_weights).tobytes())
-    for r in runs[1:]:
-        if (bytes(r.program.params.c_struct()), bytes(r.program.scenario.c_struct()), r.designer_horizon,
-                r.num_samples, as_f32(r.designer_weights).tobytes()) != sig:
-            raise ValueError("eval_weights_lockstep: the runs must share scenario, planner and designer weights")
-    lists = [[np.asarray(w, dtype=np.float64) for w in wl] for wl in weight_lists]
-    lists = [[w[0] if w.ndim == 2 else w for w in wl] for wl in lists]
+    if session is None or not session.get("checked"):
+        sig = _run_signature(ref)
+        for r in runs[1:]:
+            if _run_signature(r) != sig:
+                raise ValueError("eval_weights_lockstep: the runs must share scenario, planner and designer weights")
+        if session is not None:
+            session["checked"] = True
+    K = ref.program.params.K
+    lists = [_candidate_rows(wl, K) for wl in weight_lists]
     active = [i for i, wl in enumerate(lists) if len(wl)]
     if not active:
         return [np.zeros(0) for _ in runs]
-    batches = {i: runs[i]._episode_batch(lists[i]) for i in active}
-    off, Ws, robots, widxs, uls = 0, [], [], [], []
+    raw = np.concatenate([lists[i] for i in active])                   # every candidate of every active run
+    W = _planning_weight_rows(raw)                                     # what the planner gets  [sum nc, K] float32
+    unit = _unit_rows(raw)                                             # what the history records (reference :120)
+    # the episode layout of a run -- its initial states tiled over its candidates -- is kept for the session (the
+    # initial states do not change inside one optimisation); the replanning world's vanishing cars are drawn per call
+    kept = None if session is None else session.setdefault("layouts", {})
+    layouts = []
     for i in active:
-        b = batches[i]
-        Ws.append(b["W"]); robots.append(b["robot"]); widxs.append(b["widx"] + off)
-        uls.append(b["unlucky"])
-        off += b["W"].shape[0]
-    W, robot, widx = np.concatenate(Ws), np.concatenate(robots), np.concatenate(widxs).astype(np.int32)
-    unlucky = None if uls[0] is None else np.concatenate(uls).astype(np.int32)
-    eng = get_engine(ref._device)
-    p = ref.program.params
+        nc = len(lists[i])
+        l = None if kept is None else kept.get((i, nc))
+        if l is None:
+            l = runs[i]._episode_layout(nc, with_unlucky=False)
+            if kept is not None:
+                kept[(i, nc)] = l
+        layouts.append(l)
+    counts = np.array([len(lists[i]) for i in active])
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    # the flat episode batch: kept between generations while the same runs evaluate as many candidates on the same
+    # initial states (the arrays of a layout are themselves kept per run, so identity is the test)
+    cache = getattr(ref, "_lockstep_cache", None)
+    key = tuple((i, id(l["robot"]), id(l["widx"])) for i, l in zip(active, layouts))
+    if cache is None or cache["key"] != key:
+        robot = np.concatenate([l["robot"] for l in layouts])
+        widx = np.concatenate([l["widx"] + o for l, o in zip(layouts, offs)]).astype(np.int32)
+        cache = ref._lockstep_cache = dict(key=key, robot=robot, widx=widx, ri=np.ascontiguousarray(robot.T),
+                                           keep=[(l["robot"], l["widx"]) for l in layouts],      # pins the ids
+                                           structs=(ref.program.params.c_struct(), ref.program.scenario.c_struct()))
+    robot, widx = cache["robot"], cache["widx"]
+    unlucky = None
+    if ref.program.replanning:
+        # the reference resets the world once per (candidate, init, sample), serially, and every reset toggles the
+        # vanishing car (reference :87-89, replanning_world.py:19-27): each run's sequence runs over all ITS resets
+        unlucky = np.concatenate([unlucky_sequence(runs[i].world, l["robot"].shape[0])
+                                  for i, l in zip(active, layouts)]).astype(np.int32)
+    p, sc = ref.program.params, ref.program.scenario
+    tw = as_f32(ref.designer_weights)
+    B = robot.shape[0]
     if _par.world()[1] > 1:
         import torch
-        B = robot.shape[0]
+        eng = get_engine(ref._device)
 
         def run(idx):
-            o = eng.episodes(p, ref.program.scenario, robot[idx], W, as_f32(ref.designer_weights), ref.designer_horizon,
-                             weight_idx=widx[idx], unlucky_idx=None if unlucky is None else unlucky[idx],
-                             final_world=True)
+            o = eng.episodes(p, sc, robot[idx], W, tw, ref.designer_horizon, weight_idx=widx[idx],
+                             unlucky_idx=None if unlucky is None else unlucky[idx], final_world=True)
             return torch.cat([o["returns"][:, None], o["final_world"].reshape(len(idx), -1)], dim=1)
 
         rows = _par.sharded_rows(run, B).cpu().numpy()
+        ret, fw = np.ascontiguousarray(rows[:, 0]), rows[:, 1:].reshape(B, p.C, 4)
     else:
-        import torch
-        o = eng.episodes(p, ref.program.scenario, robot, W, as_f32(ref.designer_weights), ref.designer_horizon,
-                         weight_idx=widx, unlucky_idx=unlucky, final_world=True)
-        rows = torch.cat([o["returns"][:, None], o["final_world"].reshape(robot.shape[0], -1)], dim=1).cpu().numpy()
+        from ...runtime import get_host_context
+        ret, fw = get_host_context(ref._device).episodes_soa(
+            p, sc, cache["ri"], np.ascontiguousarray(W.T), tw, ref.designer_horizon, weight_idx=widx,
+            unlucky_idx=unlucky, final_world=True, structs=cache["structs"])
+        fw = np.moveaxis(fw, -1, 0)                                      # [C, 4, B] -> [B, C, 4]
     ref.kernel_launches += 1
     out, at = [np.zeros(0) for _ in runs], 0
-    for i in active:
-        b = batches[i]
-        n = b["robot"].shape[0]
-        part = rows[at:at + n]
+    for j, i in enumerate(active):
+        l = layouts[j]
+        n = l["robot"].shape[0]
+        lo, hi = offs[j], offs[j + 1]
+        if session is None:
+            runs[i]._after_episodes(dict(W=W[lo:hi], I=l["I"]), fw[at + n - 1])
+        else:
+            session.setdefault("state", {})[i] = (W[hi - 1].copy(), l["I"], fw[at + n - 1].copy())
+        out[i] = runs[i]._record(None, ret[at:at + n].reshape(l["shape"]), unit[lo:hi])
         at += n
-        runs[i]._after_episodes(b, part[-1, 1:].reshape(p.C, 4))
-        out[i] = runs[i]._record(lists[i], np.ascontiguousarray(part[:, 0]).reshape(b["shape"]))
     return out
+
+
+def finish_lockstep_session(runs: Sequence["MPC_ORD"], session: dict) -> None:
+    """Write the object state eval_weights_lockstep parked in `session`: every run is left as its last evaluation
+    would have left it."""
+    runs = list(runs)
+    for i, (w_last, I, fw) in session.pop("state", {}).items():
+        runs[i]._after_episodes(dict(W=w_last[None], I=I), fw)
 
 
 def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sigma0=0.1, **stop) -> list:
@@ -137,10 +216,14 @@ def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sig
         assert not r.done
         r.history.seed = seed
         r.should_save_history = True
-    eval_weights_lockstep(runs, [[r.designer_weights] for r in runs])
-    res = _cma.fmin2_lockstep(lambda pops: eval_weights_lockstep(runs, pops),
-                              [list(r.designer_weights) for r in runs], sigma0,
-                              [dict(seed=seed, **stop) for seed in seeds])
+    session = {}
+    try:
+        eval_weights_lockstep(runs, [[r.designer_weights] for r in runs], session)
+        res = _cma.fmin2_lockstep(lambda pops: eval_weights_lockstep(runs, pops, session),
+                                  [list(r.designer_weights) for r in runs], sigma0,
+                                  [dict(seed=seed, **stop) for seed in seeds])
+    finally:
+        finish_lockstep_session(runs, session)
     for r in runs:
         r.should_save_history = False
         r.done = True
@@ -193,14 +276,14 @@ class MPC_ORD:
         Wm = np.atleast_2d(np.asarray(weight_matrix, dtype=np.float64))
         if Wm.ndim == 3:                                     # rows given as [1, K] (the reference passes such weights around)
             Wm = Wm[:, 0, :]
-        # _planning_weights for every row: the norms row by row (the same dot product the scalar path takes), the three
-        # divisions for all rows at once (elementwise, so the same quotients)
-        for _ in range(3):
-            Wm = Wm / np.array([math.sqrt(float(w.dot(w))) for w in Wm])[:, None]
-        W = Wm.astype(np.float32)
+        return dict(W=_planning_weight_rows(Wm), **self._episode_layout(Wm.shape[0], inits))
+
+    def _episode_layout(self, nc: int, inits: Optional[Sequence] = None, with_unlucky: bool = True) -> dict:
+        """Everything of `_episode_batch` but the weights, for nc candidates (with_unlucky=False: without drawing the
+        replanning world's vanishing cars, which advances the world's toggle -- the caller does that itself)."""
         inits = self.init_car_states if inits is None else inits
         src = np.asarray(inits, dtype=np.float64)
-        nc, ns = W.shape[0], self.num_samples
+        ns = self.num_samples
         c = self._batch_cache
         if c is None or c["nc"] != nc or c["ns"] != ns or c["src"].shape != src.shape or not np.array_equal(c["src"], src):
             I = np.stack([as_f32(s, (4,)) for s in inits])
@@ -211,11 +294,11 @@ class MPC_ORD:
         I, robot, widx = c["I"], c["robot"], c["widx"]
         ni = I.shape[0]
         unlucky = None
-        if self.program.replanning:
+        if self.program.replanning and with_unlucky:
             # the reference resets the world once per (candidate, init, sample), serially, and every reset toggles the
             # vanishing car (reference :87-89, replanning_world.py:19-27): the sequence runs over all nc*ni*ns resets
             unlucky = np.asarray(unlucky_sequence(self.world, nc * ni * ns), np.int32)
-        return dict(W=W, I=I, robot=robot, widx=widx, unlucky=unlucky, shape=(nc, ni, ns))
+        return dict(I=I, robot=robot, widx=widx, unlucky=unlucky, shape=(nc, ni, ns))
 
     def _after_episodes(self, batch: dict, final_world: np.ndarray) -> None:
         """Leave the Python objects the way a serial evaluation would: last weights, last init, final state."""
@@ -306,17 +389,19 @@ class MPC_ORD:
         W = [w[0] if w.ndim == 2 else w for w in W]
         return self._record(W, self.episode_returns(W))               # [nc, ni, ns]
 
-    def _record(self, W, ret) -> np.ndarray:
+    def _record(self, W, ret, unit=None) -> np.ndarray:
         """History / iteration bookkeeping of eval_weights (reference :128-151) for the candidates W with episode
-        returns ret [nc, ni, ns].  -> -totals."""
+        returns ret [nc, ni, ns].  `unit`: the rows w / np.linalg.norm(w) (reference :120) when the caller has them
+        already.  -> -totals."""
         totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
-        for w, total in zip(W, totals):
-            wn = w / math.sqrt(float(w.dot(w)))                  # w / np.linalg.norm(w) (reference :120) without the call overhead
+        if unit is None:
+            unit = _unit_rows(np.asarray(W, dtype=np.float64).reshape(len(totals), -1))
+        for wn, total in zip(unit, totals):
             if self.verbose:
                 print('ITERATION', self.iter)
                 print('eval', wn)
                 print('eval reward for weights:', total, '\n\n')
-            self.history.append((wn, total))
+            self.history.append((wn.copy(), total))            # its own array, like the reference's entries
             self.iter += 1
         if self.should_save_history and self.save_path is not None:
             self.save_history()
