@@ -129,29 +129,29 @@ class CMAESBatch:
         maxfevals, maxiter, tolfun, tolx = per(maxfevals), per(maxiter), per(tolfun), per(tolx)
         k = 10 + int(30 * self.N / self.lam)
         spread = np.full(A, np.inf)
-        for a, r in enumerate(idx):
-            h = self.fit_history[r]
-            if len(h) >= k:
-                spread[a] = max(h[-k:]) - min(h[-k:])
+        lens = [len(self.fit_history[r]) for r in idx]
+        if A and min(lens) == max(lens):                # runs in lock step have equally long histories: one reduction
+            if lens[0] >= k:
+                win = np.array([self.fit_history[r][-k:] for r in idx])
+                spread = win.max(axis=1) - win.min(axis=1)
+        else:
+            for a, r in enumerate(idx):
+                h = self.fit_history[r]
+                if len(h) >= k:
+                    spread[a] = max(h[-k:]) - min(h[-k:])
         C = self.C[idx]
         size = self.sigma[idx] * np.maximum(np.abs(self.pc[idx]).max(axis=1),
                                             np.sqrt(np.diagonal(C, axis1=1, axis2=2).max(axis=1)))
         D = self.D[idx]
-        out = []
-        for a in range(A):
-            r = idx[a]
-            if self.counteval[r] >= maxfevals[a]:
-                out.append("maxfevals")
-            elif self.countiter[r] >= maxiter[a]:
-                out.append("maxiter")
-            elif spread[a] < tolfun[a]:
-                out.append("tolfun")
-            elif size[a] < tolx[a]:
-                out.append("tolx")
-            elif D[a].max() > 1e7 * D[a].min():
-                out.append("conditioncov")
-            else:
-                out.append(None)
+        # the first criterion that holds names the reason (same order as the single-run chain of ifs)
+        tests = (("maxfevals", self.counteval[idx] >= maxfevals), ("maxiter", self.countiter[idx] >= maxiter),
+                 ("tolfun", spread < tolfun), ("tolx", size < tolx), ("conditioncov", D.max(axis=1) > 1e7 * D.min(axis=1)))
+        out = [None] * A
+        hit = np.zeros(A, dtype=bool)
+        for name, cond in tests:
+            for a in np.nonzero(cond & ~hit)[0]:
+                out[a] = name
+            hit |= cond
         return out
 
 

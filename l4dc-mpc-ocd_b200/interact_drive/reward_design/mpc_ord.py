@@ -182,16 +182,24 @@ def eval_weights_lockstep(runs: Sequence["MPC_ORD"], weight_lists: Sequence[Sequ
             unlucky_idx=unlucky, final_world=True, structs=cache["structs"])
         fw = np.moveaxis(fw, -1, 0)                                      # [C, 4, B] -> [B, C, 4]
     ref.kernel_launches += 1
+    # per-candidate totals: when every run has the same (candidates, inits, samples) -- lock step on equally large init
+    # groups -- one reduction for all of them (rows of ni*ns contiguous returns: the sum _record takes per run)
+    shape0 = layouts[0]["shape"]
+    totals_all = None
+    if all(l["shape"] == shape0 for l in layouts):
+        totals_all = ret.reshape(-1, shape0[1] * shape0[2]).sum(axis=1, dtype=np.float64) / ref.num_samples
     out, at = [np.zeros(0) for _ in runs], 0
+    state = None if session is None else session.setdefault("state", {})
     for j, i in enumerate(active):
         l = layouts[j]
         n = l["robot"].shape[0]
         lo, hi = offs[j], offs[j + 1]
-        if session is None:
+        if state is None:
             runs[i]._after_episodes(dict(W=W[lo:hi], I=l["I"]), fw[at + n - 1])
         else:
-            session.setdefault("state", {})[i] = (W[hi - 1].copy(), l["I"], fw[at + n - 1].copy())
-        out[i] = runs[i]._record(None, ret[at:at + n].reshape(l["shape"]), unit[lo:hi])
+            state[i] = (W[hi - 1], l["I"], fw[at + n - 1])
+        out[i] = runs[i]._record(None, None if totals_all is not None else ret[at:at + n].reshape(l["shape"]),
+                                 unit[lo:hi], None if totals_all is None else totals_all[lo:hi])
         at += n
     return out
 
@@ -201,7 +209,7 @@ def finish_lockstep_session(runs: Sequence["MPC_ORD"], session: dict) -> None:
     would have left it."""
     runs = list(runs)
     for i, (w_last, I, fw) in session.pop("state", {}).items():
-        runs[i]._after_episodes(dict(W=w_last[None], I=I), fw)
+        runs[i]._after_episodes(dict(W=w_last[None].copy(), I=I), fw.copy())
 
 
 def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sigma0=0.1, **stop) -> list:
@@ -389,20 +397,21 @@ class MPC_ORD:
         W = [w[0] if w.ndim == 2 else w for w in W]
         return self._record(W, self.episode_returns(W))               # [nc, ni, ns]
 
-    def _record(self, W, ret, unit=None) -> np.ndarray:
+    def _record(self, W, ret, unit=None, totals=None) -> np.ndarray:
         """History / iteration bookkeeping of eval_weights (reference :128-151) for the candidates W with episode
-        returns ret [nc, ni, ns].  `unit`: the rows w / np.linalg.norm(w) (reference :120) when the caller has them
-        already.  -> -totals."""
-        totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
+        returns ret [nc, ni, ns].  `unit`: the rows w / np.linalg.norm(w) (reference :120), `totals`: the per-candidate
+        sums over (ni, ns) divided by the samples, when the caller has them already.  -> -totals."""
+        if totals is None:
+            totals = ret.sum(axis=(1, 2), dtype=np.float64) / self.num_samples
         if unit is None:
             unit = _unit_rows(np.asarray(W, dtype=np.float64).reshape(len(totals), -1))
-        for wn, total in zip(unit, totals):
-            if self.verbose:
-                print('ITERATION', self.iter)
+        if self.verbose:
+            for k, (wn, total) in enumerate(zip(unit, totals)):
+                print('ITERATION', self.iter + k)
                 print('eval', wn)
                 print('eval reward for weights:', total, '\n\n')
-            self.history.append((wn.copy(), total))            # its own array, like the reference's entries
-            self.iter += 1
+        self.history.extend(zip(unit.copy(), totals))               # rows of a fresh array: nothing else refers to them
+        self.iter += len(totals)
         if self.should_save_history and self.save_path is not None:
             self.save_history()
         return -totals

@@ -444,3 +444,27 @@ def test_packaging_metadata_lists_every_subpackage():
     found = {"l4dc_mpc_ocd_b200" + "".join("." + p for p in d.parent.relative_to(src).parts)
              for d in src.rglob("__init__.py") if "csrc" not in d.parts}
     assert set(meta["packages"]) == found
+
+
+def test_row_wise_bookkeeping_equals_the_scalar_path():
+    """The lock-step evaluation normalises all candidates in one call and sums all runs' returns in one reduction;
+    both must give, bit for bit, what the per-candidate / per-run code of a serial evaluation gives (np.vecdot runs the
+    same BLAS dot np.linalg.norm takes per vector; a reduction over the trailing axes is the per-row one)."""
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import mpc_ord as M
+    rng = np.random.default_rng(11)
+    for K in (6, 7):
+        W = rng.normal(size=(500, K)) * np.exp(rng.normal(size=(500, 1)) * 4)
+        unit = M._unit_rows(W)
+        plan = M._planning_weight_rows(W)
+        for w, u, p in zip(W, unit, plan):
+            assert np.array_equal(u, w / np.linalg.norm(w))
+            assert np.array_equal(p.view(np.int32), M.MPC_ORD._planning_weights(w).view(np.int32))
+            x = w
+            for _ in range(3):
+                x = x / np.linalg.norm(x)                       # the reference's three normalisations, literally
+            assert np.array_equal(p, x.astype(np.float32))
+    for ni, ns in ((5, 1), (10, 1), (5, 2), (32, 1)):
+        ret = (rng.normal(size=(7, 9, ni, ns)) * 30).astype(np.float32)
+        one = ret.reshape(-1, ni * ns).sum(axis=1, dtype=np.float64).reshape(7, 9)
+        for r in range(7):
+            assert np.array_equal(one[r], ret[r].sum(axis=(1, 2), dtype=np.float64))
