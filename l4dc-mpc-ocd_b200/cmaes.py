@@ -13,8 +13,8 @@ The state lives in `CMAESBatch`: R independent runs of the same dimension and po
 separate worker processes (experiments/run_mpc_ord.py:83-90); in lock step on one GPU their Python bookkeeping,
 not the episode launch, is what a generation costs, so it must not be a loop over runs.  Every operation is
 row-wise (stacked matmul / eigh, reductions along the last axes, one RandomState per run), so a run's trajectory
-does not depend on which other runs share the batch; `CMAES`, the single-run class, is a batch of one and therefore
-takes bit for bit the steps the same run takes inside a larger batch."""
+does not depend on which other runs share the batch, and it is bit for bit the trajectory of `CMAES`, the plain
+single-run class."""
 from __future__ import annotations
 
 import math
@@ -26,6 +26,92 @@ import numpy as np
 def _row_norm(x: np.ndarray) -> np.ndarray:
     """np.linalg.norm of every row: sqrt(x.dot(x)) -- vecdot runs the same BLAS dot over each row."""
     return np.sqrt(np.vecdot(x, x))
+
+
+class CMAES:
+    """One run, plain 2-D numpy: what `optimize_cmaes` drives.  `CMAESBatch` below performs the same operations on stacked
+    arrays and reproduces this class bit for bit (tests/test_host_logic_cpu.py pins that on long runs; numpy applies the
+    same BLAS / LAPACK routine to every matrix of a stack)."""
+
+    def __init__(self, x0: Sequence[float], sigma0: float, seed: Optional[int] = None, popsize: Optional[int] = None):
+        self.N = N = len(x0)
+        self.mean = np.asarray(x0, dtype=np.float64).copy()
+        self.sigma = float(sigma0)
+        self.rng = np.random.RandomState(None if seed is None else int(seed) % (2 ** 32))
+        self.lam = popsize or 4 + int(3 * math.log(N))
+        self.mu = self.lam // 2
+        w = math.log(self.lam / 2 + 0.5) - np.log(np.arange(1, self.mu + 1))
+        self.weights = w / w.sum()
+        self.mueff = 1.0 / np.sum(self.weights ** 2)
+        self.cc = (4 + self.mueff / N) / (N + 4 + 2 * self.mueff / N)
+        self.cs = (self.mueff + 2) / (N + self.mueff + 5)
+        self.c1 = 2 / ((N + 1.3) ** 2 + self.mueff)
+        self.cmu = min(1 - self.c1, 2 * (self.mueff - 2 + 1 / self.mueff) / ((N + 2) ** 2 + self.mueff))
+        self.damps = 1 + 2 * max(0.0, math.sqrt((self.mueff - 1) / (N + 1)) - 1) + self.cs
+        self.chiN = math.sqrt(N) * (1 - 1 / (4 * N) + 1 / (21 * N * N))
+        self.pc, self.ps = np.zeros(N), np.zeros(N)
+        self.C = np.eye(N)
+        self.B, self.D = np.eye(N), np.ones(N)
+        self.invsqrtC = np.eye(N)
+        self.countiter = 0
+        self.counteval = 0
+        self._eigeneval = 0
+        self._pop = None
+        self.best_x, self.best_f = self.mean.copy(), np.inf
+        self.fit_history = []
+
+    def ask(self) -> np.ndarray:
+        """-> population [lambda, N]."""
+        z = self.rng.standard_normal((self.lam, self.N))
+        self._pop = self.mean + self.sigma * (z * self.D) @ self.B.T
+        return self._pop.copy()
+
+    def tell(self, fitness: Sequence[float]) -> None:
+        f = np.asarray(fitness, dtype=np.float64)
+        N, pop = self.N, self._pop
+        self.counteval += len(f)
+        self.countiter += 1
+        order = np.argsort(f, kind="stable")
+        if f[order[0]] < self.best_f:
+            self.best_f, self.best_x = float(f[order[0]]), pop[order[0]].copy()
+        self.fit_history.append(float(f[order[0]]))
+        sel = pop[order[: self.mu]]
+        old = self.mean
+        self.mean = self.weights @ sel
+        y = (self.mean - old) / self.sigma
+        self.ps = (1 - self.cs) * self.ps + math.sqrt(self.cs * (2 - self.cs) * self.mueff) * (self.invsqrtC @ y)
+        hsig = (np.linalg.norm(self.ps) / math.sqrt(1 - (1 - self.cs) ** (2 * self.countiter)) / self.chiN
+                < 1.4 + 2 / (N + 1))
+        self.pc = (1 - self.cc) * self.pc + hsig * math.sqrt(self.cc * (2 - self.cc) * self.mueff) * y
+        art = (sel - old) / self.sigma
+        self.C = ((1 - self.c1 - self.cmu) * self.C
+                  + self.c1 * (np.outer(self.pc, self.pc) + (1 - hsig) * self.cc * (2 - self.cc) * self.C)
+                  + self.cmu * (art.T * self.weights) @ art)
+        self.sigma *= math.exp((self.cs / self.damps) * (np.linalg.norm(self.ps) / self.chiN - 1))
+        if self.counteval - self._eigeneval > self.lam / (self.c1 + self.cmu) / N / 10:
+            self._eigeneval = self.counteval
+            self.C = np.triu(self.C) + np.triu(self.C, 1).T
+            d, self.B = np.linalg.eigh(self.C)
+            self.D = np.sqrt(np.maximum(d, 1e-20))
+            self.invsqrtC = (self.B / self.D) @ self.B.T
+
+    def stop(self, maxfevals=np.inf, maxiter=None, tolfun=1e-11, tolx=1e-11) -> Optional[str]:
+        """pycma's main default termination criteria."""
+        if maxiter is None:
+            maxiter = 100 + 150 * (self.N + 3) ** 2 // math.sqrt(self.lam)
+        if self.counteval >= maxfevals:
+            return "maxfevals"
+        if self.countiter >= maxiter:
+            return "maxiter"
+        h = self.fit_history
+        k = 10 + int(30 * self.N / self.lam)
+        if len(h) >= k and max(h[-k:]) - min(h[-k:]) < tolfun:
+            return "tolfun"
+        if self.sigma * max(np.max(np.abs(self.pc)), math.sqrt(np.max(np.diag(self.C)))) < tolx:
+            return "tolx"
+        if self.D.max() > 1e7 * self.D.min():
+            return "conditioncov"
+        return None
 
 
 class CMAESBatch:
@@ -184,23 +270,6 @@ class _Run:
     best_x = property(lambda s: s._b.best_x[s._r].copy())
     best_f = property(lambda s: float(s._b.best_f[s._r]))
     fit_history = property(lambda s: s._b.fit_history[s._r])
-
-
-class CMAES(_Run):
-    """A single run: a batch of one (so it takes exactly the steps the same run takes inside a larger batch)."""
-
-    def __init__(self, x0: Sequence[float], sigma0: float, seed: Optional[int] = None, popsize: Optional[int] = None):
-        super().__init__(CMAESBatch([list(x0)], float(sigma0), [seed], popsize), 0)
-
-    def ask(self) -> np.ndarray:
-        """-> population [lambda, N]."""
-        return self._b.ask()[0]
-
-    def tell(self, fitness: Sequence[float]) -> None:
-        self._b.tell(np.asarray(fitness, dtype=np.float64)[None])
-
-    def stop(self, maxfevals=np.inf, maxiter=None, tolfun=1e-11, tolx=1e-11) -> Optional[str]:
-        return self._b.stop(None, maxfevals, maxiter, tolfun, tolx)[0]
 
 
 _STOP_KEYS = ("maxfevals", "maxiter", "tolfun", "tolx")

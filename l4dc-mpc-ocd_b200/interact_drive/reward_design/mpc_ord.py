@@ -212,19 +212,43 @@ def finish_lockstep_session(runs: Sequence["MPC_ORD"], session: dict) -> None:
         runs[i]._after_episodes(dict(W=w_last[None].copy(), I=I), fw.copy())
 
 
-def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sigma0=0.1, **stop) -> list:
+def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sigma0=0.1, shard_runs: bool = False,
+                            stats: Optional[dict] = None, **stop) -> list:
     """R independent `optimize_cmaes` runs (reference :33-45, one worker process each in the reference) advanced in
     lock step: generation g of every run that is still going is ONE episode launch.  Run r uses seeds[r]; its
     candidates, history and result are those of `runs[r].optimize_cmaes(seed=seeds[r], ...)` run alone.
+    With several ranks the episodes of every generation are sharded and all-gathered (every rank keeps all runs'
+    books); `shard_runs=True` spreads the RUNS instead -- rank k optimises runs k, k + N, ... on its own GPU with no
+    collective, which is how many runs scale end to end (a generation's cost is mostly its Python bookkeeping) -- and
+    exchanges histories, results and object state once at the end, so every rank still finishes with all of them
+    (`stats`, when given, receives the wall-clock seconds of the two phases: "optimise_s", "exchange_s").
     -> list of best weight vectors."""
     runs = list(runs)
     assert len(seeds) == len(runs)
+    rank, ws = _par.group()
+    if shard_runs and ws > 1:
+        mine = list(range(rank, len(runs), ws))
+        t0 = time.perf_counter()
+        with _par.local_only():
+            xs = optimize_cmaes_lockstep([runs[i] for i in mine], [seeds[i] for i in mine], sigma0, **stop) if mine else []
+        t1 = time.perf_counter()
+        packed = _par.all_gather_objects([(i, x, runs[i]._export_state()) for i, x in zip(mine, xs)])
+        out = [None] * len(runs)
+        for part in packed:
+            for i, x, state in part:
+                out[i] = x
+                if i not in mine:
+                    runs[i]._import_state(state)
+        if stats is not None:
+            stats.update(optimise_s=t1 - t0, exchange_s=time.perf_counter() - t1)
+        return out
     for r, seed in zip(runs, seeds):
         assert seed != 0
         assert not r.done
         r.history.seed = seed
         r.should_save_history = True
     session = {}
+    t0 = time.perf_counter()
     try:
         eval_weights_lockstep(runs, [[r.designer_weights] for r in runs], session)
         res = _cma.fmin2_lockstep(lambda pops: eval_weights_lockstep(runs, pops, session),
@@ -232,6 +256,8 @@ def optimize_cmaes_lockstep(runs: Sequence["MPC_ORD"], seeds: Sequence[int], sig
                                   [dict(seed=seed, **stop) for seed in seeds])
     finally:
         finish_lockstep_session(runs, session)
+    if stats is not None:
+        stats.update(optimise_s=time.perf_counter() - t0, exchange_s=0.0)
     for r in runs:
         r.should_save_history = False
         r.done = True
@@ -307,6 +333,29 @@ class MPC_ORD:
             # vanishing car (reference :87-89, replanning_world.py:19-27): the sequence runs over all nc*ni*ns resets
             unlucky = np.asarray(unlucky_sequence(self.world, nc * ni * ns), np.int32)
         return dict(I=I, robot=robot, widx=widx, unlucky=unlucky, shape=(nc, ni, ns))
+
+    def _export_state(self) -> dict:
+        """What an optimisation leaves in this object (for a rank that did not run it): history, counters, the
+        planner's last weights / initial state, the world's final state and the replanning toggle."""
+        # the history as two arrays, not thousands of small ones: pickling it is what the exchange costs
+        hist = (np.stack([np.asarray(w, dtype=np.float64) for w, _ in self.history]) if len(self.history) else np.zeros((0, self.weight_dim)),
+                np.array([v for _, v in self.history], dtype=np.float64))
+        return dict(history=hist, seed=getattr(self.history, "seed", None), iter=self.iter, done=self.done,
+                    launches=self.kernel_launches, weights=np.asarray(self.car.weights), init=np.asarray(self.car.init_state),
+                    states=[np.asarray(c.state) for c in self.world.cars],
+                    unlucky=getattr(self.world, "unlucky_car_idx", None))
+
+    def _import_state(self, st: dict) -> None:
+        self.history[:] = list(zip(st["history"][0], st["history"][1]))
+        if st["seed"] is not None:
+            self.history.seed = st["seed"]
+        self.iter, self.done, self.kernel_launches = st["iter"], st["done"], st["launches"]
+        self.car.weights_f32 = as_f32(st["weights"])
+        self.car.init_state = st["init"]
+        for c, s in zip(self.world.cars, st["states"]):
+            c.state = s
+        if st["unlucky"] is not None:
+            self.world.unlucky_car_idx = st["unlucky"]
 
     def _after_episodes(self, batch: dict, final_world: np.ndarray) -> None:
         """Leave the Python objects the way a serial evaluation would: last weights, last init, final state."""

@@ -13,11 +13,47 @@ import torch
 import torch.distributed as dist
 
 
+_local_only = 0
+
+
 def world() -> Tuple[int, int]:
-    """(rank, world_size) of the default process group; (0, 1) outside torch.distributed."""
+    """(rank, world_size) of the default process group; (0, 1) outside torch.distributed, and inside `local_only()`."""
+    if not _local_only and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def group() -> Tuple[int, int]:
+    """(rank, world_size) of the default process group, `local_only()` or not."""
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+class local_only:
+    """Inside this context the sharding helpers see a world of one: work whose UNITS are spread over the ranks by the
+    caller (independent optimisation runs, a rank's own subset each) is evaluated entirely on this rank's GPU, with no
+    collective -- the caller exchanges results once, at the end."""
+
+    def __enter__(self):
+        global _local_only
+        _local_only += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _local_only
+        _local_only -= 1
+        return False
+
+
+def all_gather_objects(obj) -> list:
+    """Every rank's `obj`, in rank order, on every rank (pickled; for end-of-run results, not for the data path)."""
+    rank, ws = group()
+    if ws == 1:
+        return [obj]
+    out = [None] * ws
+    dist.all_gather_object(out, obj)
+    return out
 
 
 def shard_bounds(B: int, rank: int, world_size: int) -> Tuple[int, int, int]:

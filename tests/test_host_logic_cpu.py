@@ -468,3 +468,33 @@ def test_row_wise_bookkeeping_equals_the_scalar_path():
         one = ret.reshape(-1, ni * ns).sum(axis=1, dtype=np.float64).reshape(7, 9)
         for r in range(7):
             assert np.array_equal(one[r], ret[r].sum(axis=(1, 2), dtype=np.float64))
+
+
+def test_cmaes_batch_reproduces_the_single_run_class_bit_for_bit():
+    """`CMAESBatch` (stacked arrays, what the lock-step optimisation drives) against `CMAES` (plain 2-D numpy, what
+    `optimize_cmaes` drives): populations, means, step sizes and covariance matrices stay bit-identical over long runs,
+    with the runs of the batch asked / told in changing subsets."""
+    def ell(x):
+        n = len(x)
+        return float(sum((10.0 ** (3.0 * i / (n - 1))) * x[i] ** 2 for i in range(n)))
+    for N in (6, 7):
+        x0 = list(np.linspace(-0.5, 0.5, N))
+        seeds = [1, 2, 3, 12345, 77]
+        singles = [cmaes.CMAES(x0, 0.05, seed=s) for s in seeds]
+        batch = cmaes.CMAESBatch([x0] * len(seeds), 0.05, seeds)
+        for g in range(120):
+            idx = np.array([r for r in range(len(seeds)) if (g + r) % 4 != 0 or g < 10])      # a changing subset
+            pops = batch.ask(idx)
+            fits = []
+            for r, pb in zip(idx, pops):
+                ps = singles[r].ask()
+                assert np.array_equal(ps, pb)
+                fit = [ell(x) for x in ps]
+                singles[r].tell(fit)
+                fits.append(fit)
+            batch.tell(np.array(fits), idx)
+            for r in idx:
+                s = singles[r]
+                assert s.sigma == batch.sigma[r] and np.array_equal(s.mean, batch.mean[r])
+                assert np.array_equal(s.C, batch.C[r]) and np.array_equal(s.invsqrtC, batch.invsqrtC[r])
+            assert batch.stop(idx, maxiter=100) == [singles[r].stop(maxiter=100) for r in idx]
