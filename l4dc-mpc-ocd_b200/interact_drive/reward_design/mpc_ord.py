@@ -277,7 +277,9 @@ class MPC_ORD:
         w = np.asarray(car.weights)
         self.designer_weights = w / np.linalg.norm(w)
         self.weight_dim = len(w)
-        self.history = list2()
+        self._history = list2()
+        self._history_blocks = []       # the same entries as per-generation (weights [n, K], totals [n]) blocks, see _record
+        self._history_pending = None    # a history received from another rank, not yet turned into list entries
         self.iter = 0
         self.should_save_history = False
         self.done = False
@@ -334,21 +336,46 @@ class MPC_ORD:
             unlucky = np.asarray(unlucky_sequence(self.world, nc * ni * ns), np.int32)
         return dict(I=I, robot=robot, widx=widx, unlucky=unlucky, shape=(nc, ni, ns))
 
+    @property
+    def history(self) -> list2:
+        """The reference's history: a list of (normalised weights, -objective) tuples, `history.seed` beside it.  A history
+        received from another rank (`_import_state`) becomes list entries the first time someone looks."""
+        if self._history_pending is not None:
+            (W, v), self._history_pending = self._history_pending, None
+            self._history[:] = list(zip(W, v))
+            self._history_blocks = [(W, v)]
+        return self._history
+
+    @history.setter
+    def history(self, value) -> None:
+        self._history, self._history_blocks, self._history_pending = value, [], None
+
+    def _history_arrays(self):
+        """The history as (weights [n, K], totals [n]): the per-generation blocks `_record` keeps when they still
+        describe the list (nobody appended to or cut the list behind its back), else read off the list."""
+        if self._history_pending is not None:
+            return self._history_pending
+        h = self._history
+        if sum(len(v) for _, v in self._history_blocks) == len(h) and len(h):
+            return (np.concatenate([W for W, _ in self._history_blocks]), np.concatenate([v for _, v in self._history_blocks]))
+        if not len(h):
+            return np.zeros((0, self.weight_dim)), np.zeros(0)
+        return (np.stack([np.asarray(w, dtype=np.float64) for w, _ in h]), np.array([v for _, v in h], dtype=np.float64))
+
     def _export_state(self) -> dict:
         """What an optimisation leaves in this object (for a rank that did not run it): history, counters, the
         planner's last weights / initial state, the world's final state and the replanning toggle."""
-        # the history as two arrays, not thousands of small ones: pickling it is what the exchange costs
-        hist = (np.stack([np.asarray(w, dtype=np.float64) for w, _ in self.history]) if len(self.history) else np.zeros((0, self.weight_dim)),
-                np.array([v for _, v in self.history], dtype=np.float64))
-        return dict(history=hist, seed=getattr(self.history, "seed", None), iter=self.iter, done=self.done,
+        # the history as two arrays, not thousands of small ones: building, pickling and rebuilding the list is what the
+        # exchange would cost otherwise
+        return dict(history=self._history_arrays(), seed=getattr(self._history, "seed", None), iter=self.iter, done=self.done,
                     launches=self.kernel_launches, weights=np.asarray(self.car.weights), init=np.asarray(self.car.init_state),
                     states=[np.asarray(c.state) for c in self.world.cars],
                     unlucky=getattr(self.world, "unlucky_car_idx", None))
 
     def _import_state(self, st: dict) -> None:
-        self.history[:] = list(zip(st["history"][0], st["history"][1]))
+        self._history_pending = st["history"]                   # list entries are made on first access (`history`)
         if st["seed"] is not None:
-            self.history.seed = st["seed"]
+            self._history.seed = st["seed"]
         self.iter, self.done, self.kernel_launches = st["iter"], st["done"], st["launches"]
         self.car.weights_f32 = as_f32(st["weights"])
         self.car.init_state = st["init"]
@@ -459,7 +486,9 @@ class MPC_ORD:
                 print('ITERATION', self.iter + k)
                 print('eval', wn)
                 print('eval reward for weights:', total, '\n\n')
-        self.history.extend(zip(unit.copy(), totals))               # rows of a fresh array: nothing else refers to them
+        block = unit.copy()                                         # rows of a fresh array: nothing else refers to them
+        self.history.extend(zip(block, totals))
+        self._history_blocks.append((block, np.asarray(totals, dtype=np.float64)))
         self.iter += len(totals)
         if self.should_save_history and self.save_path is not None:
             self.save_history()
