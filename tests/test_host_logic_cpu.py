@@ -498,3 +498,55 @@ def test_cmaes_batch_reproduces_the_single_run_class_bit_for_bit():
                 assert s.sigma == batch.sigma[r] and np.array_equal(s.mean, batch.mean[r])
                 assert np.array_equal(s.C, batch.C[r]) and np.array_equal(s.invsqrtC, batch.invsqrtC[r])
             assert batch.stop(idx, maxiter=100) == [singles[r].stop(maxiter=100) for r in idx]
+
+
+class _OracleHostContext:
+    """Stands in for the engine's host context (`ocd_episode_batch_host`) on CPU: same SoA call, oracle episodes."""
+
+    def __init__(self, O, spec):
+        self.O, self.spec = O, spec
+
+    def episodes_soa(self, p, sc, robot_init, plan_weights, true_weights, T, weight_idx=None, unlucky_idx=None,
+                     final_world=False, **_):
+        ri = np.ascontiguousarray(np.asarray(robot_init, np.float32).T)
+        W = np.asarray(plan_weights, np.float32).T[np.asarray(weight_idx)]
+        ret = self.O.episode_batch(self.spec.params, self.spec.scenario, ri, W, np.asarray(true_weights, np.float32), T,
+                                   nthreads=2)
+        fw = np.zeros((p.C, 4, ri.shape[0]), np.float32)
+        fw[0] = ri.T
+        return (ret, fw) if final_world else ret
+
+
+def test_lockstep_host_bookkeeping_equals_serial_runs(monkeypatch):
+    """The host side of `optimize_cmaes_lockstep` (stacked CMA-ES state, one normalisation for all candidates, totals in
+    one reduction, object state written at the end) against the same runs done one after the other with
+    `optimize_cmaes` -- histories, iteration counters, results and the state left in the car, bit for bit.  Episodes come
+    from the CPU oracle behind the host-context interface, so this guards the Python bookkeeping without a GPU."""
+    import oracle as O
+    import l4dc_mpc_ocd_b200.runtime as RT
+    from l4dc_mpc_ocd_b200.interact_drive.reward_design import mpc_ord as M
+    spec = O.scenario_params("finite_horizon")
+    monkeypatch.setattr(RT, "get_host_context", lambda device=None: _OracleHostContext(O, spec))
+    monkeypatch.setattr(M, "get_engine", lambda device=None: None)      # asked for, never used on these paths
+    _, _, inits = M.finite_horizon_env(env_seeds=[1000000 + i for i in range(6)], debug=False)
+
+    def fresh():
+        runs = []
+        for g in (inits[0:2], inits[2:4], inits[4:6]):
+            car, world, _ = M.finite_horizon_env(debug=False)
+            runs.append(M.MPC_ORD(world, car, g, 3, verbose=False))
+        return runs
+
+    seeds = [5, 6, 7]
+    serial = fresh()
+    xs = [r.optimize_cmaes(seed=s, sigma0=0.05, maxfevals=27) for r, s in zip(serial, seeds)]
+    lock = fresh()
+    xl = M.optimize_cmaes_lockstep(lock, seeds, sigma0=0.05, maxfevals=27)
+    for a, b, xa, xb in zip(serial, lock, xs, xl):
+        assert np.array_equal(xa, xb) and a.iter == b.iter == 28 and b.done
+        assert len(a.history) == len(b.history) == 28
+        for (wa, va), (wb, vb) in zip(a.history, b.history):
+            assert np.array_equal(wa, wb) and va == vb
+        assert np.array_equal(a.car.weights, b.car.weights) and np.array_equal(a.car.init_state, b.car.init_state)
+        assert np.array_equal(a.world.cars[0].state, b.world.cars[0].state)
+    assert lock[0].kernel_launches == 1 + 3 and all(r.kernel_launches == 1 + 3 for r in serial)
