@@ -277,9 +277,12 @@ class MPC_ORD:
         w = np.asarray(car.weights)
         self.designer_weights = w / np.linalg.norm(w)
         self.weight_dim = len(w)
+        # the history is kept as per-evaluation blocks (weights [n, K], totals [n]) and turned into the reference's list
+        # of tuples when someone looks (`history`): an optimisation appends thousands of entries nobody reads until
+        # the end, and with many runs in lock step the list bookkeeping was a fifth of a generation's host time
         self._history = list2()
-        self._history_blocks = []       # the same entries as per-generation (weights [n, K], totals [n]) blocks, see _record
-        self._history_pending = None    # a history received from another rank, not yet turned into list entries
+        self._history_blocks = []
+        self._history_listed = 0        # blocks already in the list
         self.iter = 0
         self.should_save_history = False
         self.done = False
@@ -338,28 +341,27 @@ class MPC_ORD:
 
     @property
     def history(self) -> list2:
-        """The reference's history: a list of (normalised weights, -objective) tuples, `history.seed` beside it.  A history
-        received from another rank (`_import_state`) becomes list entries the first time someone looks."""
-        if self._history_pending is not None:
-            (W, v), self._history_pending = self._history_pending, None
-            self._history[:] = list(zip(W, v))
-            self._history_blocks = [(W, v)]
+        """The reference's history: a list of (normalised weights, -objective) tuples, `history.seed` beside it; entries
+        recorded (or received from another rank) since the last look are added now."""
+        if self._history_listed < len(self._history_blocks):
+            for W, v in self._history_blocks[self._history_listed:]:
+                self._history.extend(zip(W, v))
+            self._history_listed = len(self._history_blocks)
         return self._history
 
     @history.setter
     def history(self, value) -> None:
-        self._history, self._history_blocks, self._history_pending = value, [], None
+        self._history, self._history_blocks, self._history_listed = value, [], 0
 
     def _history_arrays(self):
-        """The history as (weights [n, K], totals [n]): the per-generation blocks `_record` keeps when they still
-        describe the list (nobody appended to or cut the list behind its back), else read off the list."""
-        if self._history_pending is not None:
-            return self._history_pending
-        h = self._history
-        if sum(len(v) for _, v in self._history_blocks) == len(h) and len(h):
+        """The history as (weights [n, K], totals [n]): the blocks, when they still describe the list (nobody appended to
+        or cut the list behind its back), else read off the list."""
+        listed = sum(len(v) for _, v in self._history_blocks[:self._history_listed])
+        if listed == len(self._history):
+            if not self._history_blocks:
+                return np.zeros((0, self.weight_dim)), np.zeros(0)
             return (np.concatenate([W for W, _ in self._history_blocks]), np.concatenate([v for _, v in self._history_blocks]))
-        if not len(h):
-            return np.zeros((0, self.weight_dim)), np.zeros(0)
+        h = self.history
         return (np.stack([np.asarray(w, dtype=np.float64) for w, _ in h]), np.array([v for _, v in h], dtype=np.float64))
 
     def _export_state(self) -> dict:
@@ -373,7 +375,8 @@ class MPC_ORD:
                     unlucky=getattr(self.world, "unlucky_car_idx", None))
 
     def _import_state(self, st: dict) -> None:
-        self._history_pending = st["history"]                   # list entries are made on first access (`history`)
+        del self._history[:]
+        self._history_blocks, self._history_listed = [st["history"]], 0      # list entries are made on first access
         if st["seed"] is not None:
             self._history.seed = st["seed"]
         self.iter, self.done, self.kernel_launches = st["iter"], st["done"], st["launches"]
@@ -486,9 +489,8 @@ class MPC_ORD:
                 print('ITERATION', self.iter + k)
                 print('eval', wn)
                 print('eval reward for weights:', total, '\n\n')
-        block = unit.copy()                                         # rows of a fresh array: nothing else refers to them
-        self.history.extend(zip(block, totals))
-        self._history_blocks.append((block, np.asarray(totals, dtype=np.float64)))
+        # rows of a fresh array (nothing else refers to them); `history` turns the block into list entries on demand
+        self._history_blocks.append((unit.copy(), np.asarray(totals, dtype=np.float64)))
         self.iter += len(totals)
         if self.should_save_history and self.save_path is not None:
             self.save_history()
